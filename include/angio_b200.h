@@ -1,0 +1,195 @@
+/*
+ * angio_b200.h -- C ABI of libangio_b200.so, the B200 (sm_100a) implementation of the
+ * kirstenmaas/nerf-for-angiography training / rendering hot path.
+ *
+ * The reference has no FFI of its own: its hot path is a sequence of Python calls into torch,
+ * nerfacc and torch_scatter (nerf/run_nerf_acc.py:284-307).  Each entry point below names the
+ * reference call it replaces.  The Python package nerf_for_angiography_b200 binds these with
+ * ctypes; nothing here mentions torch.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller allocates and owns every buffer (including workspaces); nothing is retained;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit sync;
+ *   - return value: 0 = OK, >0 = cudaError_t, <0 = ANGIO_ERR_*; angio_last_error_string() gives
+ *     a thread-local description of the last failure;
+ *   - sample arrays are "packed by ray": samples of ray r occupy [offsets[r], offsets[r+1]) in
+ *     ascending t, rays in ascending order (nerfacc's packed layout).
+ */
+#ifndef ANGIO_B200_H
+#define ANGIO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANGIO_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define ANGIO_API __attribute__((visibility("default")))
+#else
+#define ANGIO_API
+#endif
+
+#define ANGIO_ERR_INVALID_ARG (-1)
+#define ANGIO_ERR_UNSUPPORTED (-2)
+#define ANGIO_ERR_WORKSPACE (-3)
+
+ANGIO_API int angio_version(void);
+ANGIO_API const char* angio_last_error_string(void);
+/* number of SMs of the current device (grid sizing for persistent kernels) */
+ANGIO_API int angio_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cone-beam ray generation.   Replaces phantomdata/helpers.py:156-175 (get_ray_values) + the
+ * .float() cast at nerf/run_nerf_acc.py:88-89 / visualization/visualization.py:330-331.
+ * cam2world: [n_views,4,4] float64 row-major (source_matrix output, proj_helpers.py:68-77).
+ * Arithmetic is float64 in the reference's operation order, rounded once to float32.
+ *   image mode : view_ids == NULL -> rays of view `view0`, pixel order row-major [H, W] (n = W*H)
+ *   gather mode: view_ids/px/py [n] int32 (px = column = x_position, py = row = y_position)
+ * pixels (optional): [n_views, H, W] float32 -> pix_out[n] (gather of the target value).
+ */
+ANGIO_API int angio_raygen(const double* cam2world, int32_t view0, const int32_t* view_ids, const int32_t* px,
+                 const int32_t* py, int64_t n, int32_t img_w, int32_t img_h, double focal,
+                 const float* pixels, float* rays_o, float* rays_d, float* pix_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy-grid ray marching.   Replaces nerfacc.ray_marching's slab test + two-pass
+ * _C.ray_marching (called at nerf/nerf_helpers_acc.py:29).  binary: [res,res,res] uint8 (torch.bool),
+ * x-major.  roi / aabb: 6 floats (min xyz, max xyz) on the HOST.
+ */
+/* pass 0+1: t_min/t_max per ray (slab test clamped to [near,far]) and per-ray sample counts */
+ANGIO_API int angio_march_count(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host,
+                      const float* roi_host, int32_t res, const uint8_t* binary, float near_plane,
+                      float far_plane, float step_size, float* t_min, float* t_max, int32_t* counts,
+                      void* stream);
+/* exclusive scan: offsets[n+1] int32 (offsets[n] = total); also copies the total to *total_out if not NULL */
+ANGIO_API int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out,
+                             void* stream);
+/* pass 2: write samples.  ray_idx [n] int32, t_starts / t_ends [n] float32 */
+ANGIO_API int angio_march_write(const float* rays_o, const float* rays_d, int64_t n_rays, const float* roi_host,
+                      int32_t res, const uint8_t* binary, float step_size, const float* t_min,
+                      const float* t_max, const int32_t* offsets, int32_t* ray_idx, float* t_starts,
+                      float* t_ends, void* stream);
+/* nerfacc OccupancyGrid.query_occ (visualization/visualization.py:214): occupancy 0/1 at points [n,3] */
+ANGIO_API int angio_grid_query(const float* points, int64_t n, const float* roi_host, int32_t res,
+                     const uint8_t* binary, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Visibility filter + compaction.   Replaces nerfacc render_visibility + the three boolean-mask
+ * gathers inside nerfacc.ray_marching (after alpha_fn, nerf/nerf_helpers_acc.py:11-25).
+ * T_0 = 1, T_{i+1} = T_i * (1 - alpha_i) sequentially in fp32; keep iff T_i >= early_stop_eps and
+ * (alpha_thre <= 0 or alpha_i >= alpha_thre).
+ */
+ANGIO_API int angio_visibility_mask(const float* alphas, const int32_t* offsets, int64_t n_rays,
+                          float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts,
+                          void* stream);
+ANGIO_API int angio_compact_samples(const uint8_t* keep, const int32_t* offsets, const int32_t* new_offsets,
+                          int64_t n_rays, const float* t_starts, const float* t_ends,
+                          int32_t* ray_idx_out, float* t_starts_out, float* t_ends_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CPPN MLP (model/CPPN.py:96-131,166-222; relu, no skip, no view directions).
+ */
+typedef struct angio_mlp_desc {
+  int32_t enc;       /* 0 = none, 1 = fourier (model/CPPN.py:216-222) */
+  int32_t enc_basis; /* pos_enc_basis (L); input width = 3 + 6*L when enc != 0 */
+  int32_t width;     /* num_filters (H) */
+  int32_t n_hidden;  /* num_early_layers: number of HxH layers after the input layer */
+} angio_mlp_desc;
+
+/* Flat fp32 parameter layout (angio_mlp_param_count floats):
+ *   [fourier_coefficients (3*L) if enc] [W_0 (H x D_in)] [b_0 (H)] [W_1 (H x H)] [b_1] ... [W_n_hidden] [b_n_hidden]
+ *   [W_out (1 x H)] [b_out (1)]        every W row-major [out][in] exactly like torch.nn.Linear.weight */
+ANGIO_API int64_t angio_mlp_param_count(const angio_mlp_desc* desc);
+ANGIO_API int32_t angio_mlp_input_width(const angio_mlp_desc* desc);
+
+/* Where the MLP inputs come from.  Either explicit points, or ray samples whose midpoint
+ * x = o[idx] + d[idx] * (t0 + t1) / 2 (nerf/run_nerf_acc.py:290-292) is formed in-kernel. */
+typedef struct angio_samples {
+  int64_t n;              /* number of samples */
+  const float* points;    /* [n,3] or NULL */
+  const float* rays_o;    /* [R,3] (when points == NULL) */
+  const float* rays_d;    /* [R,3] */
+  const int32_t* ray_idx; /* [n] */
+  const float* t_starts;  /* [n] */
+  const float* t_ends;    /* [n] */
+} angio_samples;
+
+#define ANGIO_OUT_LOGIT 0 /* raw model output (CPPN.forward)                                   */
+#define ANGIO_OUT_SIGMA 1 /* sigmoid(logit): occ_eval_fn, nerf/nerf_helpers_acc.py:66-70        */
+#define ANGIO_OUT_ALPHA 2 /* 1 - exp(-sigmoid(logit)*(t1-t0)): alpha_fn, nerf_helpers_acc.py:11-25 */
+
+#define ANGIO_PREC_FP32 0 /* fp32 SIMT check mode (reference arithmetic)                        */
+#define ANGIO_PREC_BF16 1 /* bf16 tcgen05 tensor cores, fp32 accumulate                          */
+
+/* bytes of caller-provided workspace for forward / backward at n samples */
+ANGIO_API int64_t angio_mlp_workspace_bytes(const angio_mlp_desc* desc, int64_t n, int32_t precision, int32_t training);
+/* bytes of the saved-activation buffer a training forward fills for the backward */
+ANGIO_API int64_t angio_mlp_saved_bytes(const angio_mlp_desc* desc, int64_t n, int32_t precision);
+/* bytes of the packed (bf16, UMMA-swizzled) weight image used by ANGIO_PREC_BF16 */
+ANGIO_API int64_t angio_mlp_packed_bytes(const angio_mlp_desc* desc);
+/* refresh the packed weight image from the fp32 master parameters (after every optimiser step) */
+ANGIO_API int angio_mlp_pack_weights(const angio_mlp_desc* desc, const float* params, void* packed, void* stream);
+
+/* Replaces CPPN.forward / get_predictions (nerf/nerf_helpers.py:24-45).  out: [n] float32.
+ * saved != NULL makes it a training forward (activations kept for angio_mlp_backward). */
+ANGIO_API int angio_mlp_forward(const angio_mlp_desc* desc, const float* params, const void* packed,
+                      const angio_samples* in, int32_t out_mode, int32_t precision, float* out,
+                      void* saved, void* workspace, int64_t workspace_bytes, void* stream);
+/* Replaces autograd through CPPN.forward: grad_params (flat layout above) = d(sum(out*grad_out))/d(params).
+ * grad_params is OVERWRITTEN.  grad_out: [n] float32 w.r.t. the raw logit. */
+ANGIO_API int angio_mlp_backward(const angio_mlp_desc* desc, const float* params, const void* packed,
+                       const angio_samples* in, const void* saved, const float* grad_out,
+                       int32_t precision, float* grad_params, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Beer-Lambert attenuation line integral.   Replaces acc_render_volume_density
+ * (nerf/nerf_helpers_acc.py:45-63): pix[r] = prod_i exp(-sigmoid(p_i) * (t1_i - t0_i)), rays without
+ * samples render 1.  zero_mask (optional, [n] uint8): sigma forced to 0 where set (the `zero_idx` argument).
+ */
+ANGIO_API int angio_composite_forward(const float* logits, const float* t_starts, const float* t_ends,
+                            const int32_t* offsets, int64_t n_rays, const uint8_t* zero_mask, float* pix,
+                            void* stream);
+/* analytic backward: grad_logits[i] = grad_pix[r] * pix[r] * (-(t1-t0)) * s * (1 - s) */
+ANGIO_API int angio_composite_backward(const float* logits, const float* t_starts, const float* t_ends,
+                             const int32_t* offsets, int64_t n_rays, const uint8_t* zero_mask,
+                             const float* pix, const float* grad_pix, float* grad_logits, void* stream);
+/* fused training tail: composite forward + mse_loss (nerf/run_nerf_acc.py:296-298) + d(loss)/d(logits).
+ * loss_sum (1 float, must be zeroed by the caller) accumulates sum_r (pix_r - target_r)^2;
+ * grad_logits is d(mean over n_rays_total)/d(logit) (n_rays_total = global batch for data parallel). */
+ANGIO_API int angio_composite_mse_fused(const float* logits, const float* t_starts, const float* t_ends,
+                              const int32_t* offsets, int64_t n_rays, const float* target,
+                              int64_t n_rays_total, float* pix, float* grad_logits, float* loss_sum,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Occupancy-grid refresh.   Replaces nerfacc OccupancyGrid._update (reached from acc_update_n_step,
+ * nerf/nerf_helpers_acc.py:65-78).
+ */
+/* x = (cell_coords + jitter) / res mapped to the AABB; cells == NULL means all cells 0..n-1 */
+ANGIO_API int angio_grid_cell_points(const int64_t* cells, const float* jitter, int64_t n, const float* roi_host,
+                           int32_t res, float* points, void* stream);
+/* occs[cell] = max(occs[cell] * decay, occ)  (decay applied once per touched cell, max over duplicates).
+ * cells == NULL: all cells (n == n_cells, no workspace).  Otherwise workspace = ceil(n_cells/32)*4 bytes. */
+ANGIO_API int angio_grid_ema_update(float* occs, int64_t n_cells, const int64_t* cells, const float* occ, int64_t n,
+                          float decay, void* workspace, int64_t workspace_bytes, void* stream);
+/* binary = occs > min(mean(occs), occ_thre); mean_out (1 float) receives mean(occs) */
+ANGIO_API int angio_grid_threshold(const float* occs, int64_t n_cells, float occ_thre, uint8_t* binary,
+                         float* mean_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser.   Replaces torch.optim.Adam.step (nerf/run_nerf_acc.py:206,305-307) on the flat buffers.
+ * step is 1-based.  grad_scale multiplies the gradient first (1/world_size after an all-reduce sum).
+ */
+ANGIO_API int angio_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANGIO_B200_H */

@@ -1,0 +1,297 @@
+// march.cu -- occupancy-grid ray marching and sample compaction.
+// Replaces nerfacc.ray_marching's slab test and two-pass _C.ray_marching kernel, reached from
+// acc_ray_marching (/root/reference/nerf/nerf_helpers_acc.py:29).  The per-ray arithmetic mirrors
+// oracle/march_ref.c op for op: every fp32 operation individually rounded (__fadd_rn/__fmul_rn/__fdiv_rn, so
+// nvcc cannot contract into FMA), IEEE division, truncating float->int, NaN-dropping fminf/fmaxf.
+//
+// B200 mapping: marching is a data-dependent serial walk per ray (t0 <- t1 <- t0+dt must be accumulated in
+// order to stay bit-exact), so parallelism comes from rays: one thread per ray, a warp marches 32 rays in
+// lockstep.  The write pass stages each ray's samples in shared memory and the whole warp flushes one ray
+// segment at a time, so global stores are contiguous 128-byte runs instead of 32 scattered 4-byte stores.
+// The 128^3 byte grid (2 MB) stays L2-resident; output is 12 B/sample (int32 ray id + t0 + t1).
+#include "common.cuh"
+
+namespace {
+
+using angio::Roi;
+
+struct MarchParams {
+  Roi roi;
+  float ext[3];  // roi.hi - roi.lo (rounded once, as the reference recomputes it identically each time)
+  float resf;
+  int res;
+  float dt;
+};
+
+__device__ __forceinline__ void ray_aabb(const float o[3], const float d[3], const float* aabb, float& near_, float& far_) {
+  float tmin = __fdiv_rn(__fsub_rn(aabb[0], o[0]), d[0]);
+  float tmax = __fdiv_rn(__fsub_rn(aabb[3], o[0]), d[0]);
+  if (tmin > tmax) { float t = tmin; tmin = tmax; tmax = t; }
+  float tymin = __fdiv_rn(__fsub_rn(aabb[1], o[1]), d[1]);
+  float tymax = __fdiv_rn(__fsub_rn(aabb[4], o[1]), d[1]);
+  if (tymin > tymax) { float t = tymin; tymin = tymax; tymax = t; }
+  if (tmin > tymax || tymin > tmax) { near_ = 1e10f; far_ = 1e10f; return; }
+  if (tymin > tmin) tmin = tymin;
+  if (tymax < tmax) tmax = tymax;
+  float tzmin = __fdiv_rn(__fsub_rn(aabb[2], o[2]), d[2]);
+  float tzmax = __fdiv_rn(__fsub_rn(aabb[5], o[2]), d[2]);
+  if (tzmin > tzmax) { float t = tzmin; tzmin = tzmax; tzmax = t; }
+  if (tmin > tzmax || tzmin > tmax) { near_ = 1e10f; far_ = 1e10f; return; }
+  if (tzmin > tmin) tmin = tzmin;
+  if (tzmax < tmax) tmax = tzmax;
+  near_ = tmin;
+  far_ = tmax;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ bool occupied_at(float x, float y, float z, const MarchParams& p, const uint8_t* __restrict__ binary) {
+  if (x < p.roi.lo[0] || x > p.roi.hi[0] || y < p.roi.lo[1] || y > p.roi.hi[1] || z < p.roi.lo[2] || z > p.roi.hi[2])
+    return false;
+  const float ux = __fdiv_rn(__fsub_rn(x, p.roi.lo[0]), p.ext[0]);
+  const float uy = __fdiv_rn(__fsub_rn(y, p.roi.lo[1]), p.ext[1]);
+  const float uz = __fdiv_rn(__fsub_rn(z, p.roi.lo[2]), p.ext[2]);
+  const int ix = clampi(__float2int_rz(__fmul_rn(ux, p.resf)), 0, p.res - 1);
+  const int iy = clampi(__float2int_rz(__fmul_rn(uy, p.resf)), 0, p.res - 1);
+  const int iz = clampi(__float2int_rz(__fmul_rn(uz, p.resf)), 0, p.res - 1);
+  return __ldg(binary + ((int64_t)ix * p.res + iy) * p.res + iz) != 0;
+}
+
+__device__ __forceinline__ float axis_dist(float pos, float d, float inv_d, float lo, float ext, float resf) {
+  const float u = __fmul_rn(__fdiv_rn(__fsub_rn(pos, lo), ext), resf);
+  const float s = copysignf(1.0f, d);
+  const float f = floorf(__fadd_rn(__fadd_rn(u, 0.5f), __fmul_rn(0.5f, s)));
+  return __fmul_rn(__fdiv_rn(__fmul_rn(__fsub_rn(f, u), inv_d), resf), ext);
+}
+
+// Per-ray marching state machine; `advance` runs until `budget` more samples were emitted or the ray ends.
+struct Marcher {
+  float o[3], d[3], inv[3];
+  float t0, t1, tm, tmax;
+
+  __device__ __forceinline__ void init(const float* ro, const float* rd, float tmin_, float tmax_, float dt) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { o[k] = ro[k]; d[k] = rd[k]; inv[k] = __fdiv_rn(1.0f, rd[k]); }
+    tmax = tmax_;
+    t0 = tmin_;
+    t1 = __fadd_rn(t0, dt);
+    tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+  }
+  __device__ __forceinline__ bool done() const { return !(tm < tmax); }
+
+  // emits at most `budget` samples through emit(t0, t1); returns the number emitted
+  template <class Emit>
+  __device__ __forceinline__ int advance(const MarchParams& p, const uint8_t* __restrict__ binary, int budget, Emit emit) {
+    int j = 0;
+    while (tm < tmax && j < budget) {
+      const float x = __fadd_rn(o[0], __fmul_rn(tm, d[0]));
+      const float y = __fadd_rn(o[1], __fmul_rn(tm, d[1]));
+      const float z = __fadd_rn(o[2], __fmul_rn(tm, d[2]));
+      if (occupied_at(x, y, z, p, binary)) {
+        emit(j, t0, t1);
+        ++j;
+        t0 = t1;
+        t1 = __fadd_rn(t0, p.dt);
+        tm = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+      } else {
+        const float tx = axis_dist(x, d[0], inv[0], p.roi.lo[0], p.ext[0], p.resf);
+        const float ty = axis_dist(y, d[1], inv[1], p.roi.lo[1], p.ext[1], p.resf);
+        const float tz = axis_dist(z, d[2], inv[2], p.roi.lo[2], p.ext[2], p.resf);
+        const float t = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+        const float target = __fadd_rn(tm, t);
+        float _t = tm;
+        do { _t = __fadd_rn(_t, p.dt); } while (_t < target);
+        tm = _t;
+        const float h = __fmul_rn(p.dt, 0.5f);
+        t0 = __fsub_rn(tm, h);
+        t1 = __fadd_rn(tm, h);
+      }
+    }
+    return j;
+  }
+};
+
+struct Aabb6 { float v[6]; };
+
+__global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                          int64_t n_rays, Aabb6 aabb, MarchParams p,
+                                                          const uint8_t* __restrict__ binary, float near_plane,
+                                                          float far_plane, float* __restrict__ t_min,
+                                                          float* __restrict__ t_max, int32_t* __restrict__ counts) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
+  float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
+  float a, b;
+  ray_aabb(o, d, aabb.v, a, b);
+  a = a < near_plane ? near_plane : a;  // torch.clamp(t_min, min=near_plane)
+  b = b > far_plane ? far_plane : b;    // torch.clamp(t_max, max=far_plane)
+  t_min[i] = a;
+  t_max[i] = b;
+  Marcher m;
+  m.init(o, d, a, b, p.dt);
+  int total = 0;
+  while (!m.done()) total += m.advance(p, binary, 1 << 30, [](int, float, float) {});
+  counts[i] = total;
+}
+
+constexpr int kStage = 32;            // samples staged per ray per round
+constexpr int kStagePad = kStage + 1; // +1 float: lanes writing the same slot hit different banks
+constexpr int kWarpsPerBlock = 4;
+
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays, MarchParams p,
+    const uint8_t* __restrict__ binary, const float* __restrict__ t_min, const float* __restrict__ t_max,
+    const int32_t* __restrict__ offsets, int32_t* __restrict__ ray_idx, float* __restrict__ t_starts,
+    float* __restrict__ t_ends) {
+  __shared__ float s_t0[kWarpsPerBlock][32][kStagePad];
+  __shared__ float s_t1[kWarpsPerBlock][32][kStagePad];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t ray0 = (blockIdx.x * (int64_t)kWarpsPerBlock + warp) * 32;
+  if (ray0 >= n_rays) return;
+  const int64_t i = ray0 + lane;
+  const bool valid = i < n_rays;
+  Marcher m;
+  int written = 0, base = 0;
+  if (valid) {
+    float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
+    float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
+    m.init(o, d, t_min[i], t_max[i], p.dt);
+    base = offsets[i];
+  } else {
+    m.tm = 1.0f; m.tmax = 0.0f;  // done
+  }
+  float(*st0)[kStagePad] = s_t0[warp];
+  float(*st1)[kStagePad] = s_t1[warp];
+  while (__any_sync(0xffffffffu, !m.done())) {
+    int cnt = 0;
+    if (!m.done())
+      cnt = m.advance(p, binary, kStage, [&](int j, float a, float b) { st0[lane][j] = a; st1[lane][j] = b; });
+    __syncwarp();
+    // cooperative flush: one ray segment at a time, 32 consecutive samples per store instruction
+#pragma unroll 1
+    for (int r = 0; r < 32; ++r) {
+      const int c = __shfl_sync(0xffffffffu, cnt, r);
+      if (c == 0) continue;
+      const int dst = __shfl_sync(0xffffffffu, base + written, r);
+      if (lane < c) {
+        ray_idx[dst + lane] = (int32_t)(ray0 + r);
+        t_starts[dst + lane] = st0[r][lane];
+        t_ends[dst + lane] = st1[r][lane];
+      }
+    }
+    written += cnt;
+    __syncwarp();
+  }
+}
+
+// single-block exclusive scan; n is at most a few million ray counts
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                              int32_t* __restrict__ offsets, int32_t* __restrict__ total_out) {
+  __shared__ int32_t s_warp[32];
+  __shared__ int32_t s_carry;
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < n; base += 1024 * 4) {
+    // each thread owns 4 consecutive elements -> coalesced 16-byte accesses
+    const int64_t i0 = base + (int64_t)tid * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? counts[i0 + k] : 0;
+    int32_t local = v[0] + v[1] + v[2] + v[3];
+    int32_t incl = local;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      int32_t t = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int32_t w = s_warp[lane];
+      int32_t wi = w;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) {
+        int32_t t = __shfl_up_sync(0xffffffffu, wi, s);
+        if (lane >= s) wi += t;
+      }
+      s_warp[lane] = wi - w;  // exclusive prefix of warp sums
+    }
+    __syncthreads();
+    const int32_t carry = s_carry;
+    int32_t excl = carry + s_warp[warp] + incl - local;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < n) offsets[i0 + k] = excl;
+      excl += v[k];
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = excl;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    offsets[n] = s_carry;
+    if (total_out) *total_out = s_carry;
+  }
+}
+
+__global__ void __launch_bounds__(256) grid_query_kernel(const float* __restrict__ pts, int64_t n, MarchParams p,
+                                                         const uint8_t* __restrict__ binary, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = occupied_at(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], p, binary) ? 1.0f : 0.0f;
+}
+
+MarchParams make_params(const float* roi_host, int res, float dt) {
+  MarchParams p;
+  p.roi = angio::make_roi(roi_host);
+  for (int k = 0; k < 3; ++k) p.ext[k] = p.roi.hi[k] - p.roi.lo[k];
+  p.res = res;
+  p.resf = (float)res;
+  p.dt = dt;
+  return p;
+}
+
+}  // namespace
+
+extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host,
+                                 const float* roi_host, int32_t res, const uint8_t* binary, float near_plane,
+                                 float far_plane, float step_size, float* t_min, float* t_max, int32_t* counts,
+                                 void* stream) {
+  ANGIO_REQUIRE(rays_o && rays_d && aabb_host && roi_host && binary && t_min && t_max && counts, "angio_march_count: null pointer");
+  ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_count: bad sizes (step_size must be > 0)");
+  if (n_rays == 0) return 0;
+  Aabb6 aabb;
+  for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
+  march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
+      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts);
+  return angio::finish_launch("angio_march_count");
+}
+
+extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out, void* stream) {
+  ANGIO_REQUIRE(offsets && (counts || n == 0) && n >= 0, "angio_exclusive_scan_i32: bad arguments");
+  exclusive_scan_kernel<<<1, 1024, 0, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
+  return angio::finish_launch("angio_exclusive_scan_i32");
+}
+
+extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64_t n_rays, const float* roi_host, int32_t res,
+                                 const uint8_t* binary, float step_size, const float* t_min, const float* t_max,
+                                 const int32_t* offsets, int32_t* ray_idx, float* t_starts, float* t_ends, void* stream) {
+  ANGIO_REQUIRE(rays_o && rays_d && roi_host && binary && t_min && t_max && offsets && ray_idx && t_starts && t_ends,
+                "angio_march_write: null pointer");
+  ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_write: bad sizes");
+  if (n_rays == 0) return 0;
+  const int rays_per_block = 32 * kWarpsPerBlock;
+  march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
+      rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets, ray_idx, t_starts, t_ends);
+  return angio::finish_launch("angio_march_write");
+}
+
+extern "C" int angio_grid_query(const float* points, int64_t n, const float* roi_host, int32_t res, const uint8_t* binary,
+                                float* out, void* stream) {
+  ANGIO_REQUIRE(points && roi_host && binary && out && n >= 0 && res > 0, "angio_grid_query: bad arguments");
+  if (n == 0) return 0;
+  grid_query_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(points, n, make_params(roi_host, res, 1.0f), binary, out);
+  return angio::finish_launch("angio_grid_query");
+}

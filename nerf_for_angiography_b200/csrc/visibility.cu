@@ -1,0 +1,100 @@
+// visibility.cu -- transmittance-based visibility filter and stream compaction of ray samples.
+// Replaces nerfacc's render_visibility and the three boolean-mask gathers inside nerfacc.ray_marching
+// (run after alpha_fn, /root/reference/nerf/nerf_helpers_acc.py:11-25,29).
+//
+// One warp per ray.  The transmittance T_{i+1} = T_i * (1 - alpha_i) must be accumulated in sample order to
+// stay bit-identical to the serial definition, so the chain is walked with warp shuffles (every lane follows
+// the same 32-step dependent chain; lane j latches T_j) while the loads stay coalesced; thousands of rays in
+// flight hide the chain latency.  Compaction uses __ballot_sync/__popc prefix sums: the kept samples of a ray
+// are written contiguously at new_offsets[ray], no atomics.  HBM traffic: 4 B/sample in + 1 B/sample out for
+// the mask; 9 B/sample in + 12 B/kept sample out for the compaction.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) visibility_mask_kernel(const float* __restrict__ alphas,
+                                                              const int32_t* __restrict__ offsets, int64_t n_rays,
+                                                              float eps, float thre, uint8_t* __restrict__ keep,
+                                                              int32_t* __restrict__ kept_counts) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  for (int64_t r = warp_global; r < n_rays; r += n_warps) {
+    const int beg = offsets[r], end = offsets[r + 1];
+    float T = 1.0f;
+    int kept = 0;
+    for (int base = beg; base < end; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < end;
+      const float a = valid ? alphas[i] : 0.0f;
+      float myT = 1.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float aj = __shfl_sync(0xffffffffu, a, j);
+        if (lane == j) myT = T;
+        T = __fmul_rn(T, __fsub_rn(1.0f, aj));  // padded lanes multiply by exactly 1
+      }
+      bool vis = valid && (myT >= eps);
+      if (thre > 0.0f) vis = vis && (a >= thre);
+      if (valid) keep[i] = vis ? 1 : 0;
+      kept += __popc(__ballot_sync(0xffffffffu, vis));
+    }
+    if (lane == 0) kept_counts[r] = kept;
+  }
+}
+
+__global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict__ keep, const int32_t* __restrict__ offsets,
+                                                      const int32_t* __restrict__ new_offsets, int64_t n_rays,
+                                                      const float* __restrict__ t_starts, const float* __restrict__ t_ends,
+                                                      int32_t* __restrict__ ray_idx_out, float* __restrict__ t0_out,
+                                                      float* __restrict__ t1_out) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  for (int64_t r = warp_global; r < n_rays; r += n_warps) {
+    const int beg = offsets[r], end = offsets[r + 1];
+    int dst = new_offsets[r];
+    const int dst_end = new_offsets[r + 1];
+    if (dst == dst_end) continue;
+    for (int base = beg; base < end; base += 32) {
+      const int i = base + lane;
+      const bool k = (i < end) && keep[i];
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (k) {
+        const int pos = dst + __popc(m & ((1u << lane) - 1u));
+        ray_idx_out[pos] = (int32_t)r;
+        t0_out[pos] = t_starts[i];
+        t1_out[pos] = t_ends[i];
+      }
+      dst += __popc(m);
+    }
+  }
+}
+
+int warp_grid(int64_t n_rays) {
+  int64_t blocks = (n_rays + 7) / 8;  // 8 warps per 256-thread block, one ray per warp per pass
+  int64_t cap = (int64_t)angio::sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace
+
+extern "C" int angio_visibility_mask(const float* alphas, const int32_t* offsets, int64_t n_rays, float early_stop_eps,
+                                     float alpha_thre, uint8_t* keep, int32_t* kept_counts, void* stream) {
+  ANGIO_REQUIRE(offsets && kept_counts && n_rays >= 0, "angio_visibility_mask: bad arguments");
+  if (n_rays == 0) return 0;
+  visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
+                                                                                 alpha_thre, keep, kept_counts);
+  return angio::finish_launch("angio_visibility_mask");
+}
+
+extern "C" int angio_compact_samples(const uint8_t* keep, const int32_t* offsets, const int32_t* new_offsets, int64_t n_rays,
+                                     const float* t_starts, const float* t_ends, int32_t* ray_idx_out, float* t_starts_out,
+                                     float* t_ends_out, void* stream) {
+  ANGIO_REQUIRE(offsets && new_offsets && n_rays >= 0, "angio_compact_samples: bad arguments");
+  if (n_rays == 0) return 0;
+  compact_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(keep, offsets, new_offsets, n_rays, t_starts, t_ends,
+                                                                         ray_idx_out, t_starts_out, t_ends_out);
+  return angio::finish_launch("angio_compact_samples");
+}

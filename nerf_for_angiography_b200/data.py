@@ -1,0 +1,198 @@
+"""Synthetic angiography data: analytic vessel phantom -> attenuation volume -> cone-beam projections, plus the
+device-resident ray pool that replaces the reference's CSV/pandas DataFrame of precomputed rays.
+
+The reference's datasets cannot be shared (README.md:18) and its ``load_data`` is missing
+(nerf/run_nerf_acc.py:82), so the benchmark / test inputs are generated here following the reference's
+phantom pipeline (/root/reference/phantomdata/cttoray.py:189-262, helpers.py:17-18,192-224):
+volume -> trilinear interpolation along each ray -> Beer-Lambert product.  This is input preparation
+(plain torch ops on the GPU), not the hot path.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .geometry import source_matrix
+
+
+# ------------------------------------------------------------------------------------------------ phantom
+def default_capsules(seed=0):
+    """A small coronary-like tree: (p0[3], p1[3], radius) capsules inside +-60."""
+    rng = np.random.default_rng(seed)
+    caps = []
+    root = np.array([-45.0, -40.0, -30.0])
+    trunk_dir = np.array([0.6, 0.55, 0.45])
+    p = root
+    for i in range(4):
+        q = p + trunk_dir * 28 + rng.normal(0, 4, 3)
+        caps.append((p.copy(), q.copy(), 6.0 - i * 0.9))
+        # side branch
+        b = q + rng.normal(0, 1, 3) * 6 + np.array([(-1) ** i * 22.0, 12.0 * ((i % 2) * 2 - 1), 10.0])
+        caps.append((q.copy(), np.clip(b, -60, 60), 3.2 - 0.3 * i))
+        p = q
+    return [(np.clip(a, -60, 60), np.clip(b, -60, 60), float(r)) for a, b, r in caps]
+
+
+def capsule_sdf(points, capsules):
+    """Signed distance of points[N,3] to the union of capsules (negative inside)."""
+    d = None
+    for a, b, r in capsules:
+        a_t = torch.as_tensor(a, dtype=points.dtype, device=points.device)
+        b_t = torch.as_tensor(b, dtype=points.dtype, device=points.device)
+        ab = b_t - a_t
+        t = ((points - a_t) @ ab / (ab @ ab)).clamp(0, 1)
+        dist = (points - (a_t + t[:, None] * ab)).norm(dim=-1) - r
+        d = dist if d is None else torch.minimum(d, dist)
+    return d
+
+
+def rev_sigmoid(x, c1=1.0, c2=0.0):
+    """/root/reference/phantomdata/helpers.py:17-18"""
+    return 1.0 / (1.0 + torch.exp(c1 * (x - c2)))
+
+
+def make_volume(resolution=256, half_extent=100.0, kind="sdf", device="cuda", seed=0):
+    """Attenuation volume mu[res,res,res] (indexed [x,y,z]) on the +-half_extent lattice.
+
+    kind 'sdf': mu = rev_sigmoid(sdf, c1=2)           (phantomdata/helpers.py:93 convention, vessels ~1, air 0)
+    kind 'ct' : vessels + a soft-tissue ellipsoid, scaled to CT-like line integrals (configs 3-4)
+    """
+    caps = default_capsules(seed)
+    lin = torch.linspace(-half_extent, half_extent, resolution, device=device)
+    vol = torch.empty((resolution,) * 3, dtype=torch.float32, device=device)
+    for ix in range(resolution):                      # slab by slab keeps the temporary small
+        yy, zz = torch.meshgrid(lin, lin, indexing="ij")
+        pts = torch.stack([torch.full_like(yy, float(lin[ix])), yy, zz], dim=-1).reshape(-1, 3)
+        sdf = capsule_sdf(pts, caps)
+        mu = rev_sigmoid(sdf, c1=2.0)
+        if kind == "ct":
+            tissue = ((pts / torch.tensor([85.0, 70.0, 90.0], device=device)).norm(dim=-1) < 1.0).float()
+            mu = 0.12 * mu + 0.0015 * tissue
+        elif kind == "sdf":
+            mu = 0.08 * mu
+        else:
+            raise ValueError(kind)
+        vol[ix] = mu.reshape(resolution, resolution)
+    return vol
+
+
+@torch.no_grad()
+def project(volume, rays_o, rays_d, near, far, n_samples=300, half_extent=100.0, kind="ct", chunk=1 << 18):
+    """Ground-truth projector (/root/reference/phantomdata/helpers.py:192-224): trilinear lookups at evenly spaced
+    depths, I = prod exp(-mu * dt * |d|) ('ct', :208-211) or prod exp(-mu) ('sdf', :213-215)."""
+    n = rays_o.shape[0]
+    out = torch.empty(n, dtype=torch.float32, device=rays_o.device)
+    t = torch.linspace(near, far, n_samples, device=rays_o.device)
+    dt = (far - near) / (n_samples - 1)
+    vol5 = volume[None, None]                                    # [1,1,X,Y,Z]
+    for i0 in range(0, n, chunk):
+        o = rays_o[i0:i0 + chunk]
+        d = rays_d[i0:i0 + chunk]
+        pts = o[:, None, :] + d[:, None, :] * t[None, :, None]  # [m, S, 3]
+        g = (pts / half_extent).flip(-1)                         # grid_sample wants (z, y, x) order for [X,Y,Z] volumes
+        mu = torch.nn.functional.grid_sample(vol5, g[None, :, :, None, :], mode="bilinear", padding_mode="zeros",
+                                             align_corners=True)[0, 0, :, :, 0]
+        if kind == "ct":
+            tau = (mu.sum(dim=1) * dt) * d.norm(dim=-1)
+        else:
+            tau = mu.sum(dim=1)
+        out[i0:i0 + chunk] = torch.exp(-tau)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ ray pool
+class RayPool:
+    """All rays of all views, device-resident, in the compact form (cam2world[V,4,4] f64, pixels[V,H,W] f32,
+    weights[V,H,W] f32).  Replaces the reference's DataFrame of precomputed, CSV-serialised rays
+    (nerf/run_nerf_acc.py:113-117): a ray is the integer triple (view, x, y) and is expanded by the ray-generation
+    kernel when sampled."""
+
+    def __init__(self, cam2world, pixels, focal, weights=None):
+        self.cam2world = cam2world.contiguous()                 # [V,4,4] float64, CUDA
+        self.pixels = pixels.contiguous()                       # [V,H,W] float32
+        self.focal = float(focal)
+        self.n_views, self.img_h, self.img_w = pixels.shape
+        self.weights = None if weights is None else weights.contiguous().float()
+        self.n_rays = self.n_views * self.img_h * self.img_w
+        self._wsum = None
+
+    @property
+    def device(self):
+        return self.pixels.device
+
+    def rays_of_view(self, v):
+        """(o[H*W,3], d[H*W,3], pix[H*W]) of one view, pixel order row-major [y, x]."""
+        o, d = ops.raygen(self.cam2world, self.img_w, self.img_h, self.focal, view=int(v))
+        return o, d, self.pixels[int(v)].reshape(-1)
+
+    @torch.no_grad()
+    def sample_ids(self, n, weights=None, generator=None):
+        """Weighted sampling without replacement of n ray ids (exponential-race / Efraimidis-Spirakis keys with a
+        threshold pre-filter so only ~1.3 n candidates reach the top-k), then a random shuffle -- the reference's
+        ``DataFrame.sample(n, weights).sample(frac=1)`` (nerf/nerf_helpers.py:139)."""
+        N, dev = self.n_rays, self.device
+        if n > N:
+            raise ValueError("cannot sample more rays than the pool holds without replacement")
+        w = self.weights if weights is None else weights
+        u = torch.rand(N, device=dev, generator=generator).clamp_min_(1e-30)
+        keys = -torch.log(u)
+        if w is not None:
+            wf = w.reshape(-1)
+            keys = keys / wf
+            if self._wsum is None or weights is not None:
+                wsum = float(wf.sum().item())
+                if weights is None:
+                    self._wsum = wsum
+            else:
+                wsum = self._wsum
+        else:
+            wsum = float(N)
+        target = n + 6.0 * math.sqrt(n) + 16.0
+        tau = target / wsum
+        cand = torch.nonzero(keys < tau)[:, 0] if target < 0.5 * N else None
+        if cand is None or cand.numel() < n:
+            cand = torch.arange(N, device=dev)
+        sel = cand[torch.topk(keys[cand], n, largest=False).indices]
+        return sel[torch.randperm(n, device=dev, generator=generator)]
+
+    def gather(self, ids):
+        hw = self.img_h * self.img_w
+        v = (ids // hw).to(torch.int32)
+        rem = ids % hw
+        y = (rem // self.img_w).to(torch.int32)
+        x = (rem % self.img_w).to(torch.int32)
+        return ops.raygen(self.cam2world, self.img_w, self.img_h, self.focal, view_ids=v, px=x, py=y, pixels=self.pixels)
+
+    def sample(self, n, weights=None, generator=None):
+        return self.gather(self.sample_ids(n, weights=weights, generator=generator))
+
+
+def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0, 135.0), kind="ct", volume_res=128,
+                 n_proj_samples=300, src_dist=1500.0, half_extent=100.0, device="cuda", seed=0, weight_strategy="random"):
+    """Views theta in `thetas` (phi = 0) + the test view (theta, phi) LAST (the reference treats the last projection
+    as the test view and keeps it in the training pool, nerf/run_nerf_acc.py:85,114).  Focal length 7.5*W makes the
+    detector span the AABB at the isocentre.  Returns (RayPool, info dict)."""
+    focal = 7.5 * img_size
+    src = np.array([0.0, 0.0, src_dist])
+    views = [(float(t), 0.0) for t in thetas] + [tuple(map(float, test_view))]
+    mats = np.stack([source_matrix(src, th, ph, 0) for th, ph in views])
+    cam = torch.from_numpy(mats).to(device)
+    vol = make_volume(volume_res, half_extent, kind=kind, device=device, seed=seed)
+    near, far = src_dist - half_extent * 1.8, src_dist + half_extent * 1.8
+    pix = torch.empty((len(views), img_size, img_size), dtype=torch.float32, device=device)
+    for v in range(len(views)):
+        o, d = ops.raygen(cam, img_size, img_size, focal, view=v)
+        img = project(vol, o, d, near, far, n_proj_samples, half_extent, kind=kind)
+        if kind == "sdf":                                        # per-image min-max normalisation (sdftoray.py:125-126)
+            img = (img - img.min()) / (img.max() - img.min() + 1e-12)
+        pix[v] = img.view(img_size, img_size)
+    if weight_strategy == "random":                              # cttoray.py:220-221: all ones
+        weights = None
+    elif weight_strategy == "segmentation":                      # helpers.py:229-244 without the EDT: vessel pixels up-weighted
+        weights = (pix < pix.flatten(1).mean(dim=1)[:, None, None]).float() + 1e-3
+    else:
+        raise ValueError(weight_strategy)
+    info = dict(focal=focal, src_dist=src_dist, near=src_dist - half_extent, far=src_dist + half_extent, views=views,
+                half_extent=half_extent, volume=vol)
+    return RayPool(cam, pix, focal, weights), info

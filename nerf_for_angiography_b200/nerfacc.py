@@ -1,0 +1,165 @@
+"""The slice of the third-party ``nerfacc`` 0.3.x API that the reference imports
+(/root/reference/nerf/run_nerf_acc.py:12,197-198; nerf/nerf_helpers_acc.py:29,72-76;
+visualization/visualization.py:162,214), implemented on the sm_100a kernels of libangio_b200.so.
+
+    from nerf_for_angiography_b200.nerfacc import OccupancyGrid, ContractionType, ray_marching
+
+Semantics follow nerfacc 0.3.5 as restated in oracle/nerfacc_ref.py + oracle/march_ref.c (the library is not
+vendored by the reference and not installable here; see DESIGN.md "Oracle").
+"""
+import enum
+
+import torch
+
+from . import ops
+
+
+class ContractionType(enum.Enum):
+    AABB = 0
+    UN_BOUNDED_TANH = 1
+    UN_BOUNDED_SPHERE = 2
+
+
+class OccupancyGrid(torch.nn.Module):
+    """Occupancy grid with an axis-aligned ROI: ``occs`` fp32 [res^3] (EMA of the occupancy field) and
+    ``binary`` bool [res,res,res].  ``every_n_step`` refreshes it every ``n`` steps exactly like nerfacc's
+    ``OccupancyGrid._update`` (all cells during warm-up, then N/4 uniform + N/4 occupied cells)."""
+
+    NUM_DIM = 3
+
+    def __init__(self, roi_aabb, resolution=128, contraction_type=ContractionType.AABB):
+        super().__init__()
+        if contraction_type != ContractionType.AABB:
+            raise NotImplementedError("only ContractionType.AABB is used by the reference and implemented")
+        if isinstance(resolution, (list, tuple)):
+            if len(set(resolution)) != 1:
+                raise NotImplementedError("anisotropic grid resolution")
+            resolution = resolution[0]
+        self._resolution = int(resolution)
+        self.num_cells = self._resolution ** 3
+        self._contraction_type = contraction_type
+        roi = torch.as_tensor(roi_aabb, dtype=torch.float32).reshape(6).clone()
+        self.register_buffer("_roi_aabb", roi)
+        self.register_buffer("occs", torch.zeros(self.num_cells, dtype=torch.float32))
+        self.register_buffer("_binary", torch.zeros((self._resolution,) * 3, dtype=torch.bool))
+        self._roi_host = roi.cpu().numpy().copy()
+        self.occs_mean_host = 0.0   # host copy of mean(occs), refreshed by _update (read by ray_marching)
+
+    # nerfacc properties
+    @property
+    def roi_aabb(self):
+        return self._roi_aabb
+
+    @property
+    def binary(self):
+        return self._binary
+
+    @property
+    def resolution(self):
+        return torch.tensor([self._resolution] * 3, dtype=torch.int32)
+
+    @property
+    def contraction_type(self):
+        return self._contraction_type
+
+    @property
+    def device(self):
+        return self.occs.device
+
+    def _binary_u8(self):
+        b = self._binary
+        if b.dtype != torch.bool or not b.is_contiguous() or b.numel() != self.num_cells:
+            # `_binary` may have been assigned from outside (visualization.py:162)
+            b = b.to(device=self.occs.device, dtype=torch.bool).contiguous().reshape((self._resolution,) * 3)
+            self._binary = b
+        return b.view(torch.uint8)
+
+    @torch.no_grad()
+    def _sample_cells(self, step, warmup_steps, generator=None):
+        if step < warmup_steps:
+            return None                                   # all cells
+        n = self.num_cells // 4
+        dev = self.device
+        uniform = torch.randint(self.num_cells, (n,), device=dev, generator=generator)
+        occupied = torch.nonzero(self._binary.flatten())[:, 0]
+        if n < len(occupied):
+            sel = torch.randint(len(occupied), (n,), device=dev, generator=generator)
+            occupied = occupied[sel]
+        return torch.cat([uniform, occupied], dim=0)
+
+    @torch.no_grad()
+    def _update(self, step, occ_eval_fn, occ_thre=0.01, ema_decay=0.95, warmup_steps=256, cells=None, jitter=None,
+                generator=None):
+        if cells is None:
+            cells = self._sample_cells(step, warmup_steps, generator)
+        n = self.num_cells if cells is None else cells.numel()
+        if jitter is None:
+            jitter = torch.rand((n, 3), dtype=torch.float32, device=self.device, generator=generator)
+        x = ops.grid_cell_points(cells, jitter.contiguous(), self._roi_host, self._resolution)
+        occ = occ_eval_fn(x)
+        occ = occ.reshape(-1).contiguous().float()
+        ops.grid_ema_update(self.occs, cells, occ, ema_decay)
+        mean = ops.grid_threshold(self.occs, occ_thre, self._binary_u8())
+        self.occs_mean_host = float(mean.item())
+
+    @torch.no_grad()
+    def every_n_step(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, **kw):
+        if not self.training:
+            raise RuntimeError("You should only call this function only during training. Please call _update() directly "
+                               "if you want to update the field during inference.")
+        if step % n == 0 and self.training:
+            self._update(step=step, occ_eval_fn=occ_eval_fn, occ_thre=occ_thre, ema_decay=ema_decay,
+                         warmup_steps=warmup_steps, **kw)
+
+    @torch.no_grad()
+    def query_occ(self, samples):
+        pts = samples.reshape(-1, 3).contiguous().float()
+        return ops.grid_query(pts, self._roi_host, self._resolution, self._binary_u8()).reshape(samples.shape[:-1])
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._roi_host = self._roi_aabb.detach().cpu().numpy().copy()
+        return out
+
+
+def _is_fused_model(m):
+    from .model.CPPN import CPPN
+    return isinstance(m, CPPN)
+
+
+@torch.no_grad()
+def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=None, sigma_fn=None, alpha_fn=None,
+                 early_stop_eps=1e-4, alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3,
+                 stratified=False, cone_angle=0.0, radiance_field=None, return_offsets=False):
+    """nerfacc.ray_marching(...) for the argument combination the reference uses
+    (/root/reference/nerf/nerf_helpers_acc.py:29): scene_aabb + grid + alpha_fn + near/far planes.
+
+    ``radiance_field`` (extension): a CPPN whose alpha = 1 - exp(-sigmoid(f(x)) * dt) is evaluated by the fused
+    MLP kernel straight from (ray, t0, t1) -- equivalent to the reference's alpha_fn closure without
+    materialising positions.  Returns (ray_indices int64 [n], t_starts [n,1], t_ends [n,1]).
+    """
+    if t_min is not None or t_max is not None or stratified or cone_angle != 0.0 or sigma_fn is not None:
+        raise NotImplementedError("ray_marching: only the reference's call pattern is implemented "
+                                  "(scene_aabb, grid, alpha_fn, near/far planes, fixed step)")
+    if grid is None or scene_aabb is None:
+        raise NotImplementedError("ray_marching: grid and scene_aabb are required")
+    rays_o = rays_o.contiguous().float()
+    rays_d = rays_d.contiguous().float()
+    near = -1e10 if near_plane is None else float(near_plane)
+    far = 1e10 if far_plane is None else float(far_plane)
+    ray_idx, t0, t1, offsets = ops.march(rays_o, rays_d, scene_aabb, grid._roi_host, grid._resolution, grid._binary_u8(),
+                                         near, far, render_step_size)
+    have_fn = alpha_fn is not None or radiance_field is not None
+    if (alpha_thre > 0.0 or early_stop_eps > 0.0) and have_fn and ray_idx.numel() > 0:
+        if radiance_field is not None and _is_fused_model(radiance_field):
+            alphas = radiance_field.query(ops.OUT_ALPHA, rays_o=rays_o, rays_d=rays_d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+        else:
+            fn = alpha_fn
+            alphas = fn(t0[:, None], t1[:, None], ray_idx.long()).reshape(-1).contiguous().float()
+        thre = min(float(alpha_thre), float(grid.occs_mean_host))
+        ray_idx, t0, t1, offsets, _ = ops.visibility_compact(alphas, offsets, t0, t1, early_stop_eps, thre)
+    ray_indices = ray_idx.long()
+    ray_indices._angio_offsets = offsets      # packed segment offsets ride along for the compositor
+    ray_indices._angio_idx32 = ray_idx
+    out = (ray_indices, t0[:, None], t1[:, None])
+    return out + (offsets,) if return_offsets else out

@@ -1,0 +1,331 @@
+"""Validated Python entry points over the C ABI (one function per exported kernel group).
+
+Tensors are allocated by torch and passed as raw device pointers; every call is enqueued on the current
+torch CUDA stream.  Shape / dtype / device / contiguity checks happen here, before the C call.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MlpDesc, Samples, OUT_ALPHA, OUT_LOGIT, OUT_SIGMA, PREC_BF16, PREC_FP32  # noqa: F401
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name, ndim=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError(f"{name} is required")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    return t
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _host6(v, name):
+    a = np.ascontiguousarray(np.asarray(v.detach().cpu() if isinstance(v, torch.Tensor) else v, dtype=np.float32)).reshape(-1)
+    if a.size != 6:
+        raise ValueError(f"{name} must have 6 elements")
+    return a
+
+
+def sm_count() -> int:
+    return int(_lib.load().angio_sm_count())
+
+
+# ------------------------------------------------------------------------------------------------ ray generation
+def raygen(cam2world, img_w, img_h, focal, view=0, view_ids=None, px=None, py=None, pixels=None):
+    """Cone-beam rays.  Image mode (view) -> (o[H*W,3], d[H*W,3]); gather mode (view_ids, px, py) -> (o, d[, pix])."""
+    lib = _lib.load()
+    cam2world = _chk(cam2world, torch.float64, "cam2world", 3)
+    dev = cam2world.device
+    if view_ids is None:
+        n = int(img_w) * int(img_h)
+    else:
+        view_ids = _chk(view_ids, torch.int32, "view_ids", 1)
+        px = _chk(px, torch.int32, "px", 1)
+        py = _chk(py, torch.int32, "py", 1)
+        n = view_ids.numel()
+    pixels = _chk(pixels, torch.float32, "pixels", 3, allow_none=True)
+    o = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    pix = torch.empty((n,), dtype=torch.float32, device=dev) if (pixels is not None and view_ids is not None) else None
+    _lib.check(lib.angio_raygen(_p(cam2world), int(view), _p(view_ids), _p(px), _p(py), n, int(img_w), int(img_h), float(focal),
+                                _p(pixels) if pix is not None else None, _p(o), _p(d), _p(pix), _stream()), "angio_raygen")
+    return (o, d, pix) if pix is not None else (o, d)
+
+
+# ------------------------------------------------------------------------------------------------ marching
+def exclusive_scan(counts):
+    lib = _lib.load()
+    counts = _chk(counts, torch.int32, "counts", 1)
+    n = counts.numel()
+    offsets = torch.empty((n + 1,), dtype=torch.int32, device=counts.device)
+    _lib.check(lib.angio_exclusive_scan_i32(_p(counts), n, _p(offsets), None, _stream()), "angio_exclusive_scan_i32")
+    return offsets
+
+
+def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size):
+    """Two-pass occupancy-grid march.  Returns (ray_idx int32 [n], t_starts [n], t_ends [n], offsets int32 [R+1]).
+
+    One host sync (reads the total sample count to size the outputs), like the reference library.
+    """
+    lib = _lib.load()
+    rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
+    rays_d = _chk(rays_d, torch.float32, "ray_directions", 2)
+    if rays_o.shape != rays_d.shape or rays_o.shape[1] != 3:
+        raise ValueError("ray_origins / ray_directions must both be [R, 3]")
+    binary = _bin_u8(binary, resolution)
+    aabb = _host6(scene_aabb, "scene_aabb")
+    roi = _host6(roi_aabb, "roi_aabb")
+    R, dev = rays_o.shape[0], rays_o.device
+    if R == 0:
+        e = torch.empty((0,), dtype=torch.float32, device=dev)
+        return torch.empty((0,), dtype=torch.int32, device=dev), e, e.clone(), torch.zeros((1,), dtype=torch.int32, device=dev)
+    t_min = torch.empty((R,), dtype=torch.float32, device=dev)
+    t_max = torch.empty((R,), dtype=torch.float32, device=dev)
+    counts = torch.empty((R,), dtype=torch.int32, device=dev)
+    _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
+                                     float(near_plane), float(far_plane), float(step_size), _p(t_min), _p(t_max), _p(counts),
+                                     _stream()), "angio_march_count")
+    offsets = exclusive_scan(counts)
+    n = int(offsets[-1].item())
+    ray_idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    t0 = torch.empty((n,), dtype=torch.float32, device=dev)
+    t1 = torch.empty((n,), dtype=torch.float32, device=dev)
+    if n > 0:
+        _lib.check(lib.angio_march_write(_p(rays_o), _p(rays_d), R, roi.ctypes.data, int(resolution), _p(binary), float(step_size),
+                                         _p(t_min), _p(t_max), _p(offsets), _p(ray_idx), _p(t0), _p(t1), _stream()),
+                   "angio_march_write")
+    return ray_idx, t0, t1, offsets
+
+
+def _bin_u8(binary, resolution):
+    if not isinstance(binary, torch.Tensor) or not binary.is_cuda:
+        raise ValueError("grid binary must be a CUDA tensor")
+    if binary.dtype == torch.bool:
+        binary = binary.contiguous().view(torch.uint8)
+    binary = _chk(binary, torch.uint8, "binary")
+    if binary.numel() != int(resolution) ** 3:
+        raise ValueError("binary must have resolution^3 cells")
+    return binary
+
+
+def grid_query(points, roi_aabb, resolution, binary):
+    lib = _lib.load()
+    points = _chk(points, torch.float32, "points", 2)
+    binary = _bin_u8(binary, resolution)
+    roi = _host6(roi_aabb, "roi_aabb")
+    out = torch.empty((points.shape[0],), dtype=torch.float32, device=points.device)
+    _lib.check(lib.angio_grid_query(_p(points), points.shape[0], roi.ctypes.data, int(resolution), _p(binary), _p(out), _stream()),
+               "angio_grid_query")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ visibility
+def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre):
+    """Visibility mask + compaction.  Returns (ray_idx', t_starts', t_ends', offsets', keep)."""
+    lib = _lib.load()
+    alphas = _chk(alphas, torch.float32, "alphas", 1)
+    offsets = _chk(offsets, torch.int32, "offsets", 1)
+    t_starts = _chk(t_starts, torch.float32, "t_starts", 1)
+    t_ends = _chk(t_ends, torch.float32, "t_ends", 1)
+    R, n, dev = offsets.numel() - 1, alphas.numel(), alphas.device
+    keep = torch.empty((n,), dtype=torch.uint8, device=dev)
+    kept = torch.empty((R,), dtype=torch.int32, device=dev)
+    _lib.check(lib.angio_visibility_mask(_p(alphas), _p(offsets), R, float(early_stop_eps), float(alpha_thre), _p(keep), _p(kept),
+                                         _stream()), "angio_visibility_mask")
+    new_offsets = exclusive_scan(kept)
+    n2 = int(new_offsets[-1].item())
+    ray_idx = torch.empty((n2,), dtype=torch.int32, device=dev)
+    t0 = torch.empty((n2,), dtype=torch.float32, device=dev)
+    t1 = torch.empty((n2,), dtype=torch.float32, device=dev)
+    if n2 > 0:
+        _lib.check(lib.angio_compact_samples(_p(keep), _p(offsets), _p(new_offsets), R, _p(t_starts), _p(t_ends), _p(ray_idx), _p(t0),
+                                             _p(t1), _stream()), "angio_compact_samples")
+    return ray_idx, t0, t1, new_offsets, keep
+
+
+# ------------------------------------------------------------------------------------------------ composite
+def composite_forward(logits, t_starts, t_ends, offsets, zero_mask=None):
+    lib = _lib.load()
+    logits = _chk(logits, torch.float32, "predictions", 1)
+    t_starts = _chk(t_starts, torch.float32, "t_starts", 1)
+    t_ends = _chk(t_ends, torch.float32, "t_ends", 1)
+    offsets = _chk(offsets, torch.int32, "offsets", 1)
+    zero_mask = _chk(zero_mask, torch.uint8, "zero_mask", 1, allow_none=True)
+    R = offsets.numel() - 1
+    pix = torch.empty((R,), dtype=torch.float32, device=logits.device)
+    _lib.check(lib.angio_composite_forward(_p(logits), _p(t_starts), _p(t_ends), _p(offsets), R, _p(zero_mask), _p(pix), _stream()),
+               "angio_composite_forward")
+    return pix
+
+
+def composite_backward(logits, t_starts, t_ends, offsets, pix, grad_pix, zero_mask=None):
+    lib = _lib.load()
+    grad_pix = _chk(grad_pix, torch.float32, "grad_pix", 1)
+    R = offsets.numel() - 1
+    g = torch.empty_like(logits)
+    _lib.check(lib.angio_composite_backward(_p(logits), _p(t_starts), _p(t_ends), _p(offsets), R, _p(zero_mask), _p(pix), _p(grad_pix),
+                                            _p(g), _stream()), "angio_composite_backward")
+    return g
+
+
+def composite_mse_fused(logits, t_starts, t_ends, offsets, target, n_rays_total=None):
+    """Returns (pix[R], grad_logits[n], loss_sum[1])."""
+    lib = _lib.load()
+    logits = _chk(logits, torch.float32, "predictions", 1)
+    target = _chk(target, torch.float32, "target", 1)
+    R = offsets.numel() - 1
+    pix = torch.empty((R,), dtype=torch.float32, device=logits.device)
+    g = torch.empty_like(logits)
+    loss = torch.zeros((1,), dtype=torch.float32, device=logits.device)
+    _lib.check(lib.angio_composite_mse_fused(_p(logits), _p(t_starts), _p(t_ends), _p(offsets), R, _p(target),
+                                             int(n_rays_total or R), _p(pix), _p(g), _p(loss), _stream()), "angio_composite_mse_fused")
+    return pix, g, loss
+
+
+# ------------------------------------------------------------------------------------------------ MLP
+def mlp_desc(enc, enc_basis, width, n_hidden) -> MlpDesc:
+    return MlpDesc(int(enc), int(enc_basis), int(width), int(n_hidden))
+
+
+def mlp_param_count(desc) -> int:
+    n = int(_lib.load().angio_mlp_param_count(ctypes.byref(desc)))
+    if n < 0:
+        raise RuntimeError("angio_mlp_param_count: " + _lib.last_error())
+    return n
+
+
+def mlp_bf16_supported(desc) -> bool:
+    return int(_lib.load().angio_mlp_packed_bytes(ctypes.byref(desc))) > 0
+
+
+def mlp_pack(desc, params, packed=None):
+    lib = _lib.load()
+    params = _chk(params, torch.float32, "params", 1)
+    nbytes = int(lib.angio_mlp_packed_bytes(ctypes.byref(desc)))
+    if nbytes <= 0:
+        raise RuntimeError("bf16 tensor-core path does not support this MLP shape: " + _lib.last_error())
+    if packed is None or packed.numel() < nbytes:
+        packed = torch.empty((nbytes,), dtype=torch.uint8, device=params.device)
+    _lib.check(lib.angio_mlp_pack_weights(ctypes.byref(desc), _p(params), _p(packed), _stream()), "angio_mlp_pack_weights")
+    return packed
+
+
+def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None, t_ends=None):
+    if points is not None:
+        points = _chk(points, torch.float32, "points", 2)
+        if points.shape[1] != 3:
+            raise ValueError("points must be [n, 3]")
+        n = points.shape[0]
+    else:
+        rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
+        rays_d = _chk(rays_d, torch.float32, "ray_directions", 2)
+        ray_idx = _chk(ray_idx, torch.int32, "ray_idx", 1)
+        n = ray_idx.numel()
+    t_starts = _chk(t_starts, torch.float32, "t_starts", 1, allow_none=points is not None)
+    t_ends = _chk(t_ends, torch.float32, "t_ends", 1, allow_none=points is not None)
+    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends))
+    return s, n
+
+
+def mlp_forward(desc, params, packed, out_mode, precision, saved=False, **sample_kw):
+    """Returns out[n] (and the saved-activation buffer when saved=True)."""
+    lib = _lib.load()
+    params = _chk(params, torch.float32, "params", 1)
+    s, n = _samples(**sample_kw)
+    dev = params.device
+    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    saved_buf = None
+    if saved:
+        sb = int(lib.angio_mlp_saved_bytes(ctypes.byref(desc), n, precision))
+        if sb < 0:
+            raise RuntimeError("angio_mlp_saved_bytes: " + _lib.last_error())
+        saved_buf = torch.empty((max(sb, 1),), dtype=torch.uint8, device=dev)
+    wb = int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), n, precision, 0))
+    if wb < 0:
+        raise RuntimeError("angio_mlp_workspace_bytes: " + _lib.last_error())
+    ws = torch.empty((max(wb, 1),), dtype=torch.uint8, device=dev)
+    _lib.check(lib.angio_mlp_forward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), int(out_mode), int(precision),
+                                     _p(out), _p(saved_buf), _p(ws), wb, _stream()), "angio_mlp_forward")
+    return (out, saved_buf) if saved else out
+
+
+def mlp_backward(desc, params, packed, saved_buf, grad_out, precision, grad_params=None, **sample_kw):
+    lib = _lib.load()
+    params = _chk(params, torch.float32, "params", 1)
+    grad_out = _chk(grad_out, torch.float32, "grad_out", 1)
+    s, n = _samples(**sample_kw)
+    if grad_out.numel() != n:
+        raise ValueError("grad_out must have one element per sample")
+    if grad_params is None:
+        grad_params = torch.empty_like(params)
+    wb = int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), n, precision, 1))
+    if wb < 0:
+        raise RuntimeError("angio_mlp_workspace_bytes: " + _lib.last_error())
+    ws = torch.empty((max(wb, 1),), dtype=torch.uint8, device=params.device)
+    _lib.check(lib.angio_mlp_backward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), _p(saved_buf), _p(grad_out),
+                                      int(precision), _p(grad_params), _p(ws), wb, _stream()), "angio_mlp_backward")
+    return grad_params
+
+
+# ------------------------------------------------------------------------------------------------ occupancy grid
+def grid_cell_points(cells, jitter, roi_aabb, resolution):
+    lib = _lib.load()
+    jitter = _chk(jitter, torch.float32, "jitter", 2)
+    cells = _chk(cells, torch.int64, "cells", 1, allow_none=True)
+    n = jitter.shape[0]
+    roi = _host6(roi_aabb, "roi_aabb")
+    pts = torch.empty((n, 3), dtype=torch.float32, device=jitter.device)
+    _lib.check(lib.angio_grid_cell_points(_p(cells), _p(jitter), n, roi.ctypes.data, int(resolution), _p(pts), _stream()),
+               "angio_grid_cell_points")
+    return pts
+
+
+def grid_ema_update(occs, cells, occ, decay):
+    lib = _lib.load()
+    occs = _chk(occs, torch.float32, "occs", 1)
+    occ = _chk(occ, torch.float32, "occ", 1)
+    cells = _chk(cells, torch.int64, "cells", 1, allow_none=True)
+    ws, wb = None, 0
+    if cells is not None:
+        wb = ((occs.numel() + 31) // 32) * 4
+        ws = torch.empty((wb,), dtype=torch.uint8, device=occs.device)
+    _lib.check(lib.angio_grid_ema_update(_p(occs), occs.numel(), _p(cells), _p(occ), occ.numel(), float(decay), _p(ws), wb, _stream()),
+               "angio_grid_ema_update")
+
+
+def grid_threshold(occs, occ_thre, binary_u8):
+    """binary = occs > min(mean(occs), occ_thre).  Returns the device scalar mean(occs)."""
+    lib = _lib.load()
+    occs = _chk(occs, torch.float32, "occs", 1)
+    binary_u8 = _chk(binary_u8, torch.uint8, "binary")
+    mean = torch.empty((1,), dtype=torch.float32, device=occs.device)
+    ws = torch.empty((4096,), dtype=torch.uint8, device=occs.device)
+    _lib.check(lib.angio_grid_threshold(_p(occs), occs.numel(), float(occ_thre), _p(binary_u8), _p(mean), _p(ws), 4096, _stream()),
+               "angio_grid_threshold")
+    return mean
+
+
+# ------------------------------------------------------------------------------------------------ optimiser
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    lib = _lib.load()
+    for t, nme in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _chk(t, torch.float32, nme, 1)
+    _lib.check(lib.angio_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1),
+                                   float(beta2), float(eps), int(step), float(grad_scale), _stream()), "angio_adam_step")

@@ -1,0 +1,142 @@
+"""Training / evaluation loop of the reference driver (/root/reference/nerf/run_nerf_acc.py:263-328, 338-357) on the
+fused kernels, single- or multi-GPU (one process per GPU, rays sharded, gradients all-reduced with NCCL).
+
+One ``Trainer.step()`` is one reference iteration:
+  sample_pixel_rays -> acc_update_n_step (x2 grids) -> acc_ray_marching (march + no-grad MLP + visibility filter)
+  -> MLP forward on the kept samples -> Beer-Lambert composite + MSE -> backward -> Adam -> lr decay.
+Autograd is not involved: the composite/MSE tail and the MLP backward are explicit kernels on flat buffers.
+"""
+import math
+
+import torch
+
+from . import ops
+from .model.CPPN import CPPN
+from .nerfacc import ContractionType, OccupancyGrid
+
+
+class Trainer:
+    def __init__(self, model: CPPN, pool, near, far, n_rays=5625, n_steps=300, half_extent=100.0, grid_resolution=128,
+                 lr=1e-4, decay_rate=0.1, decay_steps=500000, early_stop_eps=1e-2, alpha_thre=1e-4, vessel_alpha_thre=5e-2,
+                 vessel_grid=True, seed=0, process_group=None):
+        self.model = model
+        self.pool = pool
+        self.dev = pool.device
+        self.near, self.far = float(near), float(far)
+        self.n_rays, self.n_steps = int(n_rays), int(n_steps)
+        self.step_size = (self.far - self.near) / self.n_steps            # nerf_helpers_acc.py:27
+        self.lr0, self.decay_rate, self.decay_steps = lr, decay_rate, decay_steps
+        self.early_stop_eps, self.alpha_thre, self.vessel_alpha_thre = early_stop_eps, alpha_thre, vessel_alpha_thre
+        o = half_extent
+        self.scene_aabb = torch.tensor([-o, -o, -o, o, o, o], dtype=torch.float32, device=self.dev)   # run_nerf_acc.py:196
+        self.acc_grid = OccupancyGrid(self.scene_aabb, grid_resolution, ContractionType.AABB).to(self.dev)
+        self.vessel_acc_grid = OccupancyGrid(self.scene_aabb, grid_resolution, ContractionType.AABB).to(self.dev) if vessel_grid else None
+        model._ensure_flat()
+        self.flat = model._flat
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.packed = None
+        self.n_iter = 0
+        self.lr = lr
+        self.pg = process_group
+        self.world = 1
+        self.rank = 0
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        # rays: every rank draws a different batch; grids: every rank draws the SAME cells/jitter
+        self.ray_gen = torch.Generator(device=self.dev).manual_seed(seed + 1000 * self.rank + 1)
+        self.grid_gen = torch.Generator(device=self.dev).manual_seed(seed)
+        self.last = {}
+
+    # ------------------------------------------------------------------ pieces
+    def _occ_eval(self, x):
+        return ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x)
+
+    def update_grids(self):
+        """acc_update_n_step for both grids (run_nerf_acc.py:285-286)."""
+        self.acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.alpha_thre, generator=self.grid_gen)
+        if self.vessel_acc_grid is not None:
+            self.vessel_acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.vessel_alpha_thre, generator=self.grid_gen)
+
+    def march_and_filter(self, o, d):
+        """acc_ray_marching (run_nerf_acc.py:287): returns (ray_idx int32, t0, t1, offsets, n_prefilter)."""
+        g = self.acc_grid
+        ray_idx, t0, t1, offsets = ops.march(o, d, self.scene_aabb, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far,
+                                             self.step_size)
+        n_pre = ray_idx.numel()
+        if n_pre > 0:
+            alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
+                                     rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+            thre = min(self.alpha_thre, g.occs_mean_host)
+            ray_idx, t0, t1, offsets, _ = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre)
+        return ray_idx, t0, t1, offsets, n_pre
+
+    def _refresh_packed(self):
+        if self.model._precision_id == ops.PREC_BF16:
+            self.packed = ops.mlp_pack(self.model._desc, self.flat, self.packed)
+
+    # ------------------------------------------------------------------ one reference iteration
+    def step(self, rays=None):
+        """rays: optional (o[R,3], d[R,3], target[R]) -- otherwise sampled from the pool.  Returns a dict of device
+        scalars / python ints; nothing here forces a sync beyond the two sample-count reads of the marcher."""
+        m = self.model
+        if self.flat.data_ptr() != m._flat.data_ptr():
+            raise RuntimeError("model parameters were re-allocated after the Trainer was built")
+        if rays is None:
+            o, d, target = self.pool.sample(self.n_rays, generator=self.ray_gen)
+        else:
+            o, d, target = rays
+        self._refresh_packed()
+        self.update_grids()
+        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d)
+        n_kept = ray_idx.numel()
+        R = o.shape[0]
+        if n_kept > 0:                                                      # run_nerf_acc.py:289
+            prec = m._precision_id
+            kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+            logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, **kw)
+            pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world)
+            ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, **kw)
+            if self.world > 1:
+                torch.distributed.all_reduce(self.grad, group=self.pg)      # sum of per-rank (1/global-batch)-scaled grads
+            ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1)
+            self.n_iter_adam += 1
+            self.lr = self.lr0 * (self.decay_rate ** (self.n_iter / self.decay_steps))   # run_nerf_acc.py:323-328
+            loss = loss_sum / R
+        else:
+            loss = torch.full((1,), float("nan"), device=self.dev)
+            pix = torch.ones(R, device=self.dev)
+        self.n_iter += 1
+        self.last = dict(loss=loss, n_samples_prefilter=n_pre, n_samples=n_kept, n_rays=R, pix=pix)
+        return self.last
+
+    n_iter_adam = 0
+
+    # ------------------------------------------------------------------ evaluation (run_nerf_acc.py:338-357)
+    @torch.no_grad()
+    def render_view(self, v, binary_thresh=None):
+        o, d, target = self.pool.rays_of_view(v)
+        self._refresh_packed()
+        ray_idx, t0, t1, offsets, _ = self.march_and_filter(o, d)
+        if ray_idx.numel() == 0:
+            return torch.ones_like(target), target
+        logits = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_LOGIT, self.model._precision_id,
+                                 rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+        zero = None
+        if binary_thresh is not None:
+            zero = (torch.sigmoid(logits) < binary_thresh).to(torch.uint8)
+        return ops.composite_forward(logits, t0, t1, offsets, zero), target
+
+    @torch.no_grad()
+    def evaluate(self, v=None):
+        """PSNR of the test view (the LAST view of the pool, run_nerf_acc.py:85)."""
+        v = self.pool.n_views - 1 if v is None else v
+        pix, target = self.render_view(v)
+        mse = torch.mean((pix - target) ** 2)
+        return dict(mse=float(mse), psnr=float(-10.0 * torch.log10(mse)), image=pix.view(self.pool.img_h, self.pool.img_w))
+
+
+def psnr_from_loss(loss: float) -> float:
+    return -10.0 * math.log10(loss)

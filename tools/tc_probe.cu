@@ -1,0 +1,193 @@
+// tools/tc_probe.cu -- bring-up probe for the tcgen05 building blocks used by csrc/mlp_tc.cu.
+// Each variant checks one layout/descriptor assumption against an exact integer-valued host reference
+// (or measures issue throughput).  Run one variant per process so a trap cannot poison later variants:
+//   ./tc_probe <variant>
+//     0  SS  A K-major,  B K-major      (forward GEMM view)
+//     1  TS  A in TMEM,  B K-major      (forward, activations fed back through TMEM)
+//     2  SS  A K-major,  B MN-major     (dgrad view of the same weight tile)
+//     3  SS  A MN-major, B MN-major     (wgrad view: reduction over the sample rows)
+//     4..7 throughput: 4 SS N=128, 5 TS N=128, 6 SS N=256, 7 TS N=256
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../nerf_for_angiography_b200/csrc/tc05.cuh"
+
+using namespace tc05;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
+
+static constexpr int M = 128, N = 128, K = 64;
+
+// a_img / b_img: 16 KB smem images (already swizzled).  D out: [128][128] fp32.
+__global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, const uint8_t* b_img, float* D, int variant) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;               // 16 KB
+  uint8_t* sB = smem + 16384;       // 16 KB
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 256); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem_d = tmem, tmem_a = tmem + 128;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar_load, 32768);
+    bulk_g2s(sA, a_img, 16384, &bar_load);
+    bulk_g2s(sB, b_img, 16384, &bar_load);
+  }
+  mbar_wait(&bar_load, 0);
+
+  if (variant == 1) {
+    // A K-major image in smem -> registers -> TMEM (row = lane, packed bf16x2 per column)
+    const int row = warp * 32 + lane;
+    uint32_t v[16];
+    for (int half = 0; half < 2; ++half) {
+      for (int c = 0; c < 16; ++c) {
+        int col = (half * 16 + c) * 2;
+        v[c] = *reinterpret_cast<const uint32_t*>(sA + sw128_offset(row, col));
+      }
+      tmem_st16(tmem_a + ((uint32_t)(warp * 32) << 16) + half * 16, v);
+    }
+    wait_st();
+    fence_before_sync();
+  }
+  __syncthreads();
+  fence_after_sync();
+
+  if (warp == 0 && lane == 0) {
+    const uint32_t a_mn = (variant == 3), b_mn = (variant == 2 || variant == 3);
+    const uint32_t idesc = make_idesc_bf16(M, N, a_mn, b_mn);
+    for (int k = 0; k < K / 16; ++k) {
+      // K-major: +32 B per k-step inside the 128-B row; MN-major: +16 rows * 128 B per k-step
+      uint64_t da = a_mn ? make_smem_desc_sw128(smem_u32(sA) + k * 2048, 8192, 1024)
+                         : make_smem_desc_sw128(smem_u32(sA) + k * 32, 16, 1024);
+      uint64_t db = b_mn ? make_smem_desc_sw128(smem_u32(sB) + k * 2048, 8192, 1024)
+                         : make_smem_desc_sw128(smem_u32(sB) + k * 32, 16, 1024);
+      if (variant == 1) mma_ts(tmem_d, tmem_a + k * 8, db, idesc, k > 0);
+      else mma_ss(tmem_d, da, db, idesc, k > 0);
+    }
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  fence_after_sync();
+
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+    wait_ld();
+    for (int j = 0; j < 32; ++j) D[row * N + c0 + j] = __uint_as_float(r[j]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// throughput: each CTA issues iters * 8 MMAs (K = 128 per accumulation group) and waits once at the end
+template <int NN>
+__global__ void __launch_bounds__(128, 1) perf_kernel(int iters, int ts_mode, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                 // 2 x 16 KB (K = 128)
+  uint8_t* sB = smem + 32768;         // NN rows x 128 K: 2 blocks of NN*128 B
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x / 32;
+  for (int i = threadIdx.x; i < (32768 + NN * 256) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = make_idesc_bf16(128, NN, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < 8; ++k) {
+        uint32_t a_off = (k / 4) * 16384 + (k % 4) * 32;
+        uint32_t b_off = (k / 4) * (NN * 128) + (k % 4) * 32;
+        uint64_t da = make_smem_desc_sw128(smem_u32(sA) + a_off, 16, 1024);
+        uint64_t db = make_smem_desc_sw128(smem_u32(sB) + b_off, 16, 1024);
+        if (ts_mode) mma_ts(tmem, tmem + 256 + k * 8, db, idesc, k > 0);
+        else mma_ss(tmem, da, db, idesc, k > 0);
+      }
+    }
+    mma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  fence_after_sync();
+  if (threadIdx.x == 0 && sink) sink[blockIdx.x] = 1.0f;
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }  // exact for small ints
+
+int main(int argc, char** argv) {
+  int variant = argc > 1 ? atoi(argv[1]) : 0;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s sm_%d%d SMs=%d variant=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, variant);
+
+  if (variant >= 4) {
+    const int NN = (variant >= 6) ? 256 : 128, ts = (variant & 1);
+    const int iters = 4096;
+    size_t smem = 32768 + NN * 256 + 1024;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaEventRecord(e0));
+      if (NN == 128) {
+        CK(cudaFuncSetAttribute(perf_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        perf_kernel<128><<<prop.multiProcessorCount, 128, smem>>>(iters, ts, nullptr);
+      } else {
+        CK(cudaFuncSetAttribute(perf_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        perf_kernel<256><<<prop.multiProcessorCount, 128, smem>>>(iters, ts, nullptr);
+      }
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    double flops = 2.0 * 128 * NN * 16 * 8.0 * iters * prop.multiProcessorCount;
+    printf("PERF variant=%d mode=%s N=%d: %.3f ms  %.1f TFLOP/s\n", variant, ts ? "TS" : "SS", NN, ms, flops / ms * 1e-9);
+    return 0;
+  }
+
+  // logical operands: A[m][k], B[n][k]; small integers => exact in bf16 and fp32
+  std::vector<float> A(M * K), B(N * K), Dref(M * N, 0.f);
+  srand(123 + variant);
+  for (auto& v : A) v = (float)(rand() % 5 - 2);
+  for (auto& v : B) v = (float)(rand() % 5 - 2);
+  for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) { float s = 0; for (int k = 0; k < K; ++k) s += A[m * K + k] * B[n * K + k]; Dref[m * N + n] = s; }
+
+  std::vector<uint8_t> a_img(16384, 0), b_img(16384, 0);
+  auto put = [](std::vector<uint8_t>& img, uint32_t off, float v) { uint16_t h = f2bf(v); memcpy(&img[off], &h, 2); };
+  const bool a_mn = (variant == 3), b_mn = (variant == 2 || variant == 3);
+  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) {
+    uint32_t off = a_mn ? (uint32_t)(m / 64) * 8192 + sw128_offset(k, m % 64) : sw128_offset(m, k);
+    put(a_img, off, A[m * K + k]);
+  }
+  for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) {
+    uint32_t off = b_mn ? (uint32_t)(n / 64) * 8192 + sw128_offset(k, n % 64) : sw128_offset(n, k);
+    put(b_img, off, B[n * K + k]);
+  }
+  uint8_t *da, *db; float* dD;
+  CK(cudaMalloc(&da, 16384)); CK(cudaMalloc(&db, 16384)); CK(cudaMalloc(&dD, M * N * 4));
+  CK(cudaMemcpy(da, a_img.data(), 16384, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db, b_img.data(), 16384, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xff, M * N * 4));
+  size_t smem = 32768 + 1024;
+  CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  probe_kernel<<<1, 128, smem>>>(da, db, dD, variant);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  std::vector<float> D(M * N);
+  CK(cudaMemcpy(D.data(), dD, M * N * 4, cudaMemcpyDeviceToHost));
+  int bad = 0; double maxerr = 0;
+  for (int i = 0; i < M * N; ++i) { double e = fabs((double)D[i] - Dref[i]); if (!(e <= 0)) { if (bad < 5) printf("  mismatch at m=%d n=%d got %f want %f\n", i / N, i % N, D[i], Dref[i]); ++bad; } if (e > maxerr) maxerr = e; }
+  printf("PROBE variant=%d %s  mismatches=%d maxerr=%g\n", variant, bad ? "FAIL" : "PASS", bad, maxerr);
+  return bad ? 1 : 0;
+}
