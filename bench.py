@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py -- training-throughput benchmark of the NeRF-for-angiography hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config3|config2|tiny]
+
+One "step" = one reference training iteration (/root/reference/nerf/run_nerf_acc.py:263-328): sample a ray batch,
+refresh the occupancy grids (every 16th step), march + visibility filter, MLP forward, Beer-Lambert composite + MSE,
+backward, Adam.  Default workload: BASELINE.json configs[2] ("config3": 512x512 cone-beam, 60 views + test view,
+4x128 Fourier MLP, occupancy-grid marching, 65 536 rays per GPU per step), synthetic phantom, random-init weights.
+
+Prints ONE JSON line (rank 0).  `value` = rays/s with the step's inputs resident in HBM; `e2e` = the same metric with
+each step's ray batch arriving from pinned HOST memory (the reference samples rays on the host and copies them every
+iteration, nerf/nerf_helpers.py:144-148) and the loss read back; `roofline` describes the dominant kernel (the fused
+tcgen05 MLP forward of the no-grad visibility pass); `cpu_baseline` is the oracle port timed on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (img_size, n_views(theta sweep), rays/GPU/step, volume_res, hidden layers, width, pos_enc)
+    "config3": dict(img=512, thetas=[6.0 * i for i in range(60)], rays=65536, vol=256, L=4, H=128, enc="fourier"),
+    "config2": dict(img=256, thetas=[0.0, 45.0, 90.0, 135.0], rays=65536, vol=256, L=4, H=128, enc="fourier"),
+    "tiny": dict(img=64, thetas=[22.5 * i for i in range(8)], rays=4096, vol=64, L=4, H=128, enc="fourier"),
+}
+MLP_FWD_FLOP = {("fourier", 4, 128): 139776, ("none", 4, 128): 132096}
+
+
+def model_def(w, device, precision):
+    return {'num_early_layers': w["L"], 'num_late_layers': 0, 'num_filters': w["H"], 'num_input_channels': 3,
+            'num_output_channels': 1, 'num_input_channels_views': 0, 'use_bias': True, 'pos_enc': w["enc"], 'pos_enc_basis': 5,
+            'act_func': 'relu', 'fourier_sigma': 5, 'num_img': 1, 'device': device, 'precision': precision}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_oracle_step_time(w, n_rays_cpu, steps=1, seed=0):
+    """Time the ORACLE (CPU restatement of the reference path, torch-CPU fp32 + C marcher) on a bounded sample of the
+    same workload: `n_rays_cpu` rays of view 0 against a fully occupied grid (the state the GPU benchmark is in)."""
+    import functools
+    from oracle import cppn as ocppn, geometry as ogeo, nerfacc_ref, pipeline
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = ocppn.init_params(w["L"], w["H"], w["enc"], 5, 5.0, seed=seed)
+    params = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    f = functools.partial(ocppn.cppn_forward, params, pos_enc=w["enc"], basis=5)
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    roi = np.array([-100, -100, -100, 100, 100, 100], np.float32)
+    grid = nerfacc_ref.OccupancyGrid(roi, 128)
+    grid.binary[:] = True
+    grid.occs[:] = 0.5
+    W = w["img"]
+    o, d, _ = ogeo.get_ray_values(0.0, 0.0, 0.0, [0, 0, 1500.0], W, W, 7.5 * W)
+    rng = np.random.default_rng(seed)
+    sel = rng.permutation(W * W)[:n_rays_cpu]
+    o = o.reshape(-1, 3)[sel].astype(np.float32)
+    d = d.reshape(-1, 3)[sel].astype(np.float32)
+    target = torch.from_numpy(rng.random(n_rays_cpu).astype(np.float32))
+    times, n_pre, n_kept = [], 0, 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ri, ts, te, pre = pipeline.acc_ray_marching(f, grid, roi, o, d, 300, 1400.0, 1600.0, 1e-2, 1e-4, return_prefilter=True)
+        pos = pipeline.midpoints(torch.from_numpy(o), torch.from_numpy(d), ri, torch.from_numpy(ts), torch.from_numpy(te))
+        pred = pipeline.get_predictions(f, pos, 131072)
+        pix = pipeline.acc_render_volume_density(pred, ri, torch.from_numpy(ts), torch.from_numpy(te), n_rays_cpu)
+        loss = torch.nn.functional.mse_loss(pix, target)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+        n_pre, n_kept = len(pre[0]), len(ri)
+    return float(np.mean(times)), n_pre, n_kept
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; nerfacc is CUDA-only and absent,
+    see DESIGN.md) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    n_cpu = 1024 if args.workload != "tiny" else 256
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_step_time(w, n_cpu, 1)
+    t, n_pre, n_kept = cpu_oracle_step_time(w, n_cpu, max(1, min(args.steps, 3)))
+    val = n_cpu / t
+    line = {"impl": "reference", "metric": "train_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": f"{n_cpu} rays/step of view 0, full 128^3 grid, {n_pre} marched / {n_kept} kept samples"},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{n_cpu}-ray training steps (oracle port: torch-CPU fp32 MLP + C marcher)"},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    import nerf_for_angiography_b200 as A
+    from nerf_for_angiography_b200.data import make_dataset
+    from nerf_for_angiography_b200.train import Trainer
+    lib = A._lib.load()
+
+    torch.manual_seed(0)
+    pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], test_view=(135.0, 135.0), kind="ct", volume_res=w["vol"],
+                              device=dev, seed=0)
+    model = A.CPPN(model_def(w, dev, args.precision)).to(dev)          # same seed => identical weights on every rank
+    tr = Trainer(model, pool, info["near"], info["far"], n_rays=w["rays"], seed=0)
+    R = w["rays"]
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- e2e batches: pinned host memory, one per step (reference: host-side sampling + H2D every iteration)
+    host_batches = []
+    for _ in range(args.steps + args.warmup):
+        o, d, t = pool.sample(R, generator=tr.ray_gen)
+        host_batches.append(tuple(x.cpu().pin_memory() for x in (o, d, t)))
+    torch.cuda.synchronize()
+
+    # ---------------- device-resident arm
+    for _ in range(args.warmup):
+        tr.step()
+    sync_all()
+    launches0 = int(lib.angio_launch_count())
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tr.kernel_events, tr.kernel_samples = [], []                       # event pairs around the visibility-pass MLP launch
+    n_pre_total = n_kept_total = 0
+    e0.record()
+    for _ in range(args.steps):
+        out = tr.step()
+        n_pre_total += out["n_samples_prefilter"]
+        n_kept_total += out["n_samples"]
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop()
+    launches = int(lib.angio_launch_count()) - launches0
+    kernel_ms = [a.elapsed_time(b) for a, b in tr.kernel_events]
+    kernel_n = list(tr.kernel_samples)
+    tr.kernel_events = None
+    last_loss = float(out["loss"])
+
+    # ---------------- e2e arm: host buffers in, loss out, every step
+    for i in range(args.warmup):
+        o, d, t = (x.to(dev, non_blocking=True) for x in host_batches[i])
+        float(tr.step(rays=(o, d, t))["loss"])
+    sync_all()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        o, d, t = (x.to(dev, non_blocking=True) for x in host_batches[args.warmup + i])
+        loss_host = float(tr.step(rays=(o, d, t))["loss"])            # D2H read of the step's loss
+    e3.record()
+    sync_all()
+    ms_e2e = e2.elapsed_time(e3)
+
+    t_ms = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n_pre_total, n_kept_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+        torch.distributed.all_reduce(cnt, op=torch.distributed.ReduceOp.SUM)
+    ms, ms_e2e = float(t_ms[0]), float(t_ms[1])
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        flop = MLP_FWD_FLOP.get((w["enc"], w["L"], w["H"]))
+        roofline = None
+        if kernel_ms and flop and args.precision == "bf16":
+            # the first timed step may include a grid refresh; every entry is one launch of the visibility-pass MLP
+            ach = float(np.mean([flop * n / (t * 1e-3) for n, t in zip(kernel_n, kernel_ms) if t > 0])) * 1e-12
+            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "kernel": "mlp_fwd_tc_kernel<ALPHA> (no-grad visibility pass)", "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"
+                        if peaks else "fallback", "avg_launch_ms": float(np.mean(kernel_ms)), "samples_per_launch": float(np.mean(kernel_n))}
+        cpu = None
+        if not args.no_cpu_baseline:
+            n_cpu = 1024 if args.workload != "tiny" else 256
+            t_cpu, cp, ck = cpu_oracle_step_time(w, n_cpu, 1)
+            cpu = {"value": n_cpu / t_cpu, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"one {n_cpu}-ray training step of the oracle port ({cp} marched / {ck} kept samples, {t_cpu:.1f} s)"}
+        rays = R * world * args.steps
+        line = {"metric": "train_rays_per_s", "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "detector": f"{w['img']}x{w['img']}", "views": len(w["thetas"]) + 1,
+                           "mlp": f"{w['L']}x{w['H']} {w['enc']}", "rays_per_gpu_per_step": R, "march_steps": 300, "grid": "128^3",
+                           "l2": "no flush: every step draws fresh rays and streams ~15 M marched samples (>= 250 MB of sample "
+                                 "arrays), larger than the 126 MB L2"},
+                "samples_per_s_marched": float(cnt[0]) / (ms * 1e-3), "samples_per_s_kept": float(cnt[1]) / (ms * 1e-3),
+                "clocks": clk, "gpu_launches": launches,
+                "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 28, "d2h_bytes_per_step": 4 + 8},
+                "roofline": roofline, "cpu_baseline": cpu, "final_loss": last_loss, "e2e_final_loss": loss_host}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,8 @@ ANGIO_API int angio_version(void);
 ANGIO_API const char* angio_last_error_string(void);
 /* number of SMs of the current device (grid sizing for persistent kernels) */
 ANGIO_API int angio_sm_count(void);
+/* total number of kernels this library has launched in this process (bench.py's gpu_launches) */
+ANGIO_API int64_t angio_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Cone-beam ray generation.   Replaces phantomdata/helpers.py:156-175 (get_ray_values) + the

@@ -11,6 +11,7 @@ namespace angio {
 // thread-local last-error text (angio_last_error_string)
 void set_error(const char* fmt, ...);
 int sm_count();
+void note_launch();  // counts kernel launches (angio_launch_count)
 
 inline int finish_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

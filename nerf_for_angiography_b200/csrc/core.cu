@@ -4,8 +4,11 @@
 
 #include "common.cuh"
 
+#include <atomic>
 namespace angio {
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -30,3 +33,4 @@ int sm_count() {
 extern "C" int angio_version(void) { return ANGIO_B200_VERSION; }
 extern "C" const char* angio_last_error_string(void) { return angio::g_err; }
 extern "C" int angio_sm_count(void) { return angio::sm_count(); }
+extern "C" int64_t angio_launch_count(void) { return (int64_t)angio::g_launches.load(); }

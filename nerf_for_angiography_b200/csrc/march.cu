@@ -264,14 +264,14 @@ extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64
   if (n_rays == 0) return 0;
   Aabb6 aabb;
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
-  march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
+  angio::note_launch(); march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts);
   return angio::finish_launch("angio_march_count");
 }
 
 extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out, void* stream) {
   ANGIO_REQUIRE(offsets && (counts || n == 0) && n >= 0, "angio_exclusive_scan_i32: bad arguments");
-  exclusive_scan_kernel<<<1, 1024, 0, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
+  angio::note_launch(); exclusive_scan_kernel<<<1, 1024, 0, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
   return angio::finish_launch("angio_exclusive_scan_i32");
 }
 
@@ -283,7 +283,7 @@ extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_write: bad sizes");
   if (n_rays == 0) return 0;
   const int rays_per_block = 32 * kWarpsPerBlock;
-  march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
+  angio::note_launch(); march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets, ray_idx, t_starts, t_ends);
   return angio::finish_launch("angio_march_write");
 }
@@ -292,6 +292,6 @@ extern "C" int angio_grid_query(const float* points, int64_t n, const float* roi
                                 float* out, void* stream) {
   ANGIO_REQUIRE(points && roi_host && binary && out && n >= 0 && res > 0, "angio_grid_query: bad arguments");
   if (n == 0) return 0;
-  grid_query_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(points, n, make_params(roi_host, res, 1.0f), binary, out);
+  angio::note_launch(); grid_query_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(points, n, make_params(roi_host, res, 1.0f), binary, out);
   return angio::finish_launch("angio_grid_query");
 }

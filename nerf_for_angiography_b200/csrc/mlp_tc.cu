@@ -314,23 +314,27 @@ int tc_pack_weights(const MlpLayout& L, const float* params, void* packed, cudaS
   if (!make_plan(L, &P)) { set_error("tc_pack_weights: unsupported shape"); return ANGIO_ERR_UNSUPPORTED; }
   const int n_w_elems = (16384 + P.n_hidden * 32768) / 2;
   const int total = n_w_elems > P.n_const ? n_w_elems : P.n_const;
-  pack_kernel<<<blocks_for(total, 256), 256, 0, st>>>(params, L, P, reinterpret_cast<uint8_t*>(packed));
+  angio::note_launch(); pack_kernel<<<blocks_for(total, 256), 256, 0, st>>>(params, L, P, reinterpret_cast<uint8_t*>(packed));
   return finish_launch("tc_pack_weights");
 }
 
 template <int MODE>
 static int launch_fwd(const TcPlan& P, const void* packed, const angio_samples& in, float* out, cudaStream_t st) {
   const size_t smem = (size_t)P.total_bytes + 1024;  // + slack for the 1024-byte alignment of the dynamic window
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 256);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    attr_done = true;
+  static size_t attr_smem = 0;  // per instantiation; one device per process
+  if (attr_smem < smem) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      cudaGetLastError();  // clear
+      set_error("cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_smem = smem;
   }
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
   int grid = sm_count();
   if (n_tiles < grid) grid = (int)n_tiles;
-  mlp_fwd_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
+  angio::note_launch(); mlp_fwd_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
   return finish_launch("mlp_fwd_tc_kernel");
 }
 

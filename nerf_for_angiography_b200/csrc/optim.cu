@@ -28,7 +28,7 @@ extern "C" int angio_adam_step(float* params, const float* grads, float* exp_avg
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   int blocks = angio::blocks_for(n, 256);
   int cap = angio::sm_count() * 8;
-  adam_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+  angio::note_launch(); adam_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                                 beta2, eps, (float)((double)lr / bc1), (float)sqrt(bc2), grad_scale);
   return angio::finish_launch("angio_adam_step");
 }

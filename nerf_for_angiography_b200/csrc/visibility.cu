@@ -84,7 +84,7 @@ extern "C" int angio_visibility_mask(const float* alphas, const int32_t* offsets
                                      float alpha_thre, uint8_t* keep, int32_t* kept_counts, void* stream) {
   ANGIO_REQUIRE(offsets && kept_counts && n_rays >= 0, "angio_visibility_mask: bad arguments");
   if (n_rays == 0) return 0;
-  visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
+  angio::note_launch(); visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
                                                                                  alpha_thre, keep, kept_counts);
   return angio::finish_launch("angio_visibility_mask");
 }
@@ -94,7 +94,7 @@ extern "C" int angio_compact_samples(const uint8_t* keep, const int32_t* offsets
                                      float* t_ends_out, void* stream) {
   ANGIO_REQUIRE(offsets && new_offsets && n_rays >= 0, "angio_compact_samples: bad arguments");
   if (n_rays == 0) return 0;
-  compact_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(keep, offsets, new_offsets, n_rays, t_starts, t_ends,
+  angio::note_launch(); compact_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(keep, offsets, new_offsets, n_rays, t_starts, t_ends,
                                                                          ray_idx_out, t_starts_out, t_ends_out);
   return angio::finish_launch("angio_compact_samples");
 }

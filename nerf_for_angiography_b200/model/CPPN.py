@@ -24,7 +24,7 @@ class _CPPNForward(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, model, sample_kw, *params):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = any(ctx.needs_input_grad[3:])   # grad mode is already off inside Function.forward
         prec = model._precision_id
         packed = model._packed_weights() if prec == ops.PREC_BF16 else None
         kw = sample_kw if sample_kw is not None else {"points": x}

@@ -49,6 +49,8 @@ class Trainer:
         self.ray_gen = torch.Generator(device=self.dev).manual_seed(seed + 1000 * self.rank + 1)
         self.grid_gen = torch.Generator(device=self.dev).manual_seed(seed)
         self.last = {}
+        self.kernel_events = None     # bench.py: list of (start, end) CUDA events around the visibility-pass MLP launch
+        self.kernel_samples = []
 
     # ------------------------------------------------------------------ pieces
     def _occ_eval(self, x):
@@ -67,8 +69,15 @@ class Trainer:
                                              self.step_size)
         n_pre = ray_idx.numel()
         if n_pre > 0:
+            if self.kernel_events is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
                                      rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+            if self.kernel_events is not None:
+                ev1.record()
+                self.kernel_events.append((ev0, ev1))
+                self.kernel_samples.append(n_pre)
             thre = min(self.alpha_thre, g.occs_mean_host)
             ray_idx, t0, t1, offsets, _ = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre)
         return ray_idx, t0, t1, offsets, n_pre

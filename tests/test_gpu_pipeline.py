@@ -1,0 +1,219 @@
+"""GPU parity tests of the composed hot path (reference call surface) against the CPU oracle:
+CPPN module drop-in, bf16 tensor-core MLP vs fp32, render_rays, one full training step."""
+import functools
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cppn as ocppn, geometry as ogeo, nerfacc_ref, pipeline  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def A():
+    import nerf_for_angiography_b200 as a
+    assert torch.cuda.is_available()
+    return a
+
+
+def _model_def(L, H, pos_enc, precision=None):
+    d = {'num_early_layers': L, 'num_late_layers': 0, 'num_filters': H, 'num_input_channels': 3, 'num_output_channels': 1,
+         'num_input_channels_views': 0, 'use_bias': True, 'pos_enc': pos_enc, 'pos_enc_basis': 5, 'act_func': 'relu',
+         'fourier_sigma': 5, 'num_img': 1, 'device': torch.device("cuda")}
+    if precision:
+        d['precision'] = precision
+    return d
+
+
+def _load_golden_model(A, golden_dir, tag, L, H, pos_enc, precision):
+    g = np.load(os.path.join(golden_dir, f"cppn_{tag}.npz"))
+    model = A.CPPN(_model_def(L, H, pos_enc, precision))
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd:")}
+    assert set(model.state_dict().keys()) == set(sd.keys())          # reference checkpoint keys, verbatim
+    model.load_state_dict(sd)
+    return model.to("cuda"), g
+
+
+# ------------------------------------------------------------------------------------------------ CPPN drop-in
+def test_cppn_module_matches_reference(A, golden_dir, tmp_path):
+    model, g = _load_golden_model(A, golden_dir, "fourier_4x128", 4, 128, "fourier", "fp32")
+    assert model.precision == "fp32"
+    x = torch.from_numpy(g["x"]).cuda()
+    y = model(x)
+    assert y.shape == (x.shape[0], 1)
+    ref = g["y"]
+    assert np.max(np.abs(y.detach().cpu().numpy() - ref)) <= 1e-5 * max(1.0, np.abs(ref).max())
+    (y * torch.from_numpy(g["gout"]).cuda()).sum().backward()
+    for name, p in model.named_parameters():
+        if "grad:" + name in g.files:
+            gr = g["grad:" + name]
+            assert p.grad is not None, name
+            assert np.max(np.abs(p.grad.cpu().numpy() - gr)) <= 2e-5 * max(np.abs(gr).max(), 1e-6), name
+    assert model.img1.grad is None                                    # dead parameters stay untouched (CPPN.py:134-135)
+    # get_predictions: ragged chunking gives the same values (nerf_helpers.py:31-45)
+    with torch.no_grad():
+        yc = A.get_predictions(model, x, 50)
+    assert torch.equal(yc, y.detach())
+    # save() writes the reference's checkpoint dictionary (CPPN.py:261-276)
+    f = str(tmp_path / "m.pth")
+    model.save(f, {"note": 1})
+    ck = torch.load(f, weights_only=False)
+    assert set(ck.keys()) == {"version", "parameters", "training_information", "model"}
+    m2 = A.CPPN(ck["parameters"]); m2.load_state_dict(ck["model"]); m2 = m2.to("cuda")
+    with torch.no_grad():
+        assert torch.equal(m2(x), y.detach())
+
+
+def test_cppn_rejects_unsupported_configurations(A):
+    d = _model_def(4, 128, "none"); d['act_func'] = 'sine'; d['sine_weights'] = 15
+    with pytest.raises(NotImplementedError):
+        A.CPPN(d)
+    d = _model_def(4, 128, "barf")
+    with pytest.raises(NotImplementedError):
+        A.CPPN(d)
+    m = A.CPPN(_model_def(2, 64, "none")).to("cuda")
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(4, 3))                                          # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------------------------ bf16 tcgen05 forward
+@pytest.mark.parametrize("pos_enc,n", [("fourier", 192), ("fourier", 128 * 148 * 2 * 3 + 77), ("none", 5000), ("fourier", 1)])
+def test_mlp_bf16_tensor_core_forward(A, pos_enc, n):
+    p = ocppn.init_params(4, 128, pos_enc, 5, 5.0, seed=1)
+    model = A.CPPN(_model_def(4, 128, pos_enc, "bf16"))
+    model.load_state_dict({**{k: v for k, v in p.items()}, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda")
+    assert model.precision == "bf16"
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(n, 3, generator=g) * 2 - 1) * 100.0
+    with torch.no_grad():
+        ref = ocppn.cppn_forward(p, x, pos_enc, 5).reshape(-1).numpy()
+        y = model(x.cuda()).reshape(-1).cpu().numpy()
+        sig = model.query(A.ops.OUT_SIGMA, points=x.cuda().contiguous()).cpu().numpy()
+    scale = max(np.abs(ref).max(), 1e-3)
+    err = np.abs(y - ref).max() / scale
+    assert err <= 2e-2, err                                           # bf16 operands, fp32 accumulate: <= 2e-2 of output scale
+    assert np.abs(sig - 1 / (1 + np.exp(-ref))).max() <= 5e-3
+
+
+def test_mlp_bf16_ray_sample_inputs_and_alpha(A):
+    p = ocppn.init_params(4, 128, "fourier", 5, 5.0, seed=2)
+    model = A.CPPN(_model_def(4, 128, "fourier", "bf16"))
+    model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda")
+    rng = np.random.default_rng(0)
+    R, n = 64, 10000
+    o = (rng.normal(size=(R, 3)) * 5 + [0, 0, 1500]).astype(np.float32)
+    d = (rng.normal(size=(R, 3)) * 0.05 + [0, 0, -1]).astype(np.float32)
+    ri = np.sort(rng.integers(0, R, n)).astype(np.int32)
+    t0 = (1400 + rng.random(n) * 199).astype(np.float32); t1 = (t0 + 2.0 / 3.0).astype(np.float32)
+    pos = pipeline.midpoints(torch.from_numpy(o), torch.from_numpy(d), ri, torch.from_numpy(t0)[:, None], torch.from_numpy(t1)[:, None])
+    with torch.no_grad():
+        logit = ocppn.cppn_forward(p, pos, "fourier", 5).reshape(-1)
+        alpha = (1 - torch.exp(-torch.sigmoid(logit) * torch.from_numpy(t1 - t0))).numpy()
+    kw = dict(rays_o=torch.from_numpy(o).cuda(), rays_d=torch.from_numpy(d).cuda(), ray_idx=torch.from_numpy(ri).cuda(),
+              t_starts=torch.from_numpy(t0).cuda(), t_ends=torch.from_numpy(t1).cuda())
+    got = model.query(A.ops.OUT_ALPHA, **kw).cpu().numpy()
+    assert np.abs(got - alpha).max() <= 5e-3
+    got_l = model.query(A.ops.OUT_LOGIT, **kw).cpu().numpy()
+    assert np.abs(got_l - logit.numpy()).max() <= 2e-2 * max(1.0, np.abs(logit.numpy()).max())
+
+
+# ------------------------------------------------------------------------------------------------ render_rays / training step
+def _small_scene(A, res=32, W=24, seed=0):
+    """oracle grid (numpy) + identical GPU grid, a handful of views' rays"""
+    rng = np.random.default_rng(seed)
+    roi = np.array([-100, -100, -100, 100, 100, 100], np.float32)
+    r = np.arange(res)
+    X, Y, Z = np.meshgrid(r, r, r, indexing="ij")
+    binary = ((X - res / 2) ** 2 + (Y - res / 2) ** 2 + (Z - res / 2) ** 2 < (res / 3) ** 2)
+    og = nerfacc_ref.OccupancyGrid(roi, res); og.binary = binary; og.occs[:] = 0.02
+    gg = A.OccupancyGrid(torch.tensor(roi), res, A.ContractionType.AABB).cuda()
+    gg._binary = torch.from_numpy(binary).cuda(); gg.occs.fill_(0.02); gg.occs_mean_host = 0.02
+    os_, ds_ = [], []
+    for th, ph in ((0.0, 0.0), (60.0, 0.0), (135.0, 135.0)):
+        o, d, _ = ogeo.get_ray_values(th, ph, 0.0, [0, 0, 1500.0], W, W, 7.5 * W)
+        os_.append(o.reshape(-1, 3)); ds_.append(d.reshape(-1, 3))
+    o = np.concatenate(os_).astype(np.float32); d = np.concatenate(ds_).astype(np.float32)
+    sel = rng.permutation(len(o))[:1024]
+    return og, gg, roi, o[sel], d[sel]
+
+
+def _scaled_params(L, H, pos_enc, seed):
+    """random init, output bias shifted so sigma ~ 0.02-0.1: rays keep tens of samples before early stop"""
+    p = ocppn.init_params(L, H, pos_enc, 5, 0.05, seed=seed)
+    p["output_linear.0.bias"] = p["output_linear.0.bias"] - 3.0
+    return p
+
+
+@pytest.mark.parametrize("precision,L,H,pos_enc", [("fp32", 2, 64, "none"), ("fp32", 4, 128, "fourier"), ("bf16", 4, 128, "fourier")])
+def test_render_rays_vs_oracle(A, precision, L, H, pos_enc):
+    og, gg, roi, o, d = _small_scene(A)
+    p = _scaled_params(L, H, pos_enc, 5)
+    model = A.CPPN(_model_def(L, H, pos_enc, precision))
+    model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda")
+    f = functools.partial(ocppn.cppn_forward, p, pos_enc=pos_enc, basis=5)
+    with torch.no_grad():
+        pix_ref, (ri, ts, te) = pipeline.render_rays(f, og, roi, o, d, 300, 1400.0, 1600.0, 1e-2, 1e-4)
+    oc, dc = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    with torch.no_grad():
+        pix, (gi, g0, g1) = A.render_rays(model, gg, torch.tensor(roi).cuda(), oc, dc, 300, 1400.0, 1600.0, 1e-2, 1e-4)
+    assert gi.dtype == torch.int64 and g0.shape == (len(gi), 1)
+    pix, pix_ref = pix.cpu().numpy(), pix_ref.numpy()
+    if precision == "fp32":
+        # sample set: identical up to visibility decisions that sit within 1 ulp of the threshold
+        assert abs(len(gi) - len(ri)) <= max(2, int(1e-4 * len(ri)))
+        if len(gi) == len(ri):
+            assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(g0.cpu().numpy(), ts) and np.array_equal(g1.cpu().numpy(), te)
+        assert np.max(np.abs(pix - pix_ref)) <= 1e-5                 # fp32 check mode: <= 1e-5 on the projection
+    else:
+        # bf16 MLP: <= 1e-2 relative error on the projection, measured against the image scale (pixels live in [0, 1])
+        # and as a relative L2 norm; per-pixel ratios on nearly black pixels (value 0.01) only amplify 1e-4 absolute noise
+        assert np.max(np.abs(pix - pix_ref)) <= 1e-2 * pix_ref.max()
+        assert np.linalg.norm(pix - pix_ref) / np.linalg.norm(pix_ref) <= 1e-2
+        bright = pix_ref > 0.1
+        assert np.max(np.abs(pix - pix_ref)[bright] / pix_ref[bright]) <= 1e-2
+
+
+def test_training_step_vs_oracle_fp32(A):
+    """one reference iteration (march, filter, forward, composite, mse, backward, Adam) on fixed rays"""
+    from nerf_for_angiography_b200.train import Trainer
+    from nerf_for_angiography_b200.data import RayPool
+    og, gg, roi, o, d = _small_scene(A, seed=3)
+    L, H, pos_enc = 2, 64, "fourier"
+    p = _scaled_params(L, H, pos_enc, 7)
+    target = np.random.default_rng(1).random(len(o)).astype(np.float32)
+    # oracle step (torch CPU autograd + torch.optim.Adam)
+    params = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    f = functools.partial(ocppn.cppn_forward, params, pos_enc=pos_enc, basis=5)
+    opt = torch.optim.Adam(list(params.values()), lr=1e-4)
+    pix_ref, (ri, ts, te) = pipeline.render_rays(f, og, roi, o, d, 300, 1400.0, 1600.0, 1e-2, 1e-4)
+    loss_ref = torch.nn.functional.mse_loss(pix_ref, torch.from_numpy(target))
+    opt.zero_grad(); loss_ref.backward(); opt.step()
+    # B200 step
+    model = A.CPPN(_model_def(L, H, pos_enc, "fp32"))
+    model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda")
+    dummy_pool = RayPool(torch.eye(4, dtype=torch.float64).cuda()[None], torch.zeros(1, 2, 2).cuda(), 1.0)
+    tr = Trainer(model, dummy_pool, 1400.0, 1600.0, n_rays=len(o), vessel_grid=False)
+    tr.acc_grid = gg
+    tr.n_iter = 1                                                      # skip the grid refresh (step % 16 != 0)
+    out = tr.step(rays=(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), torch.from_numpy(target).cuda()))
+    assert abs(out["n_samples"] - len(ri)) <= 2
+    assert np.isclose(float(out["loss"]), float(loss_ref), rtol=1e-5)
+    # gradients (flat layout: coef, W0, b0, ..., W_out, b_out) before the optimiser touched them
+    order = (["fourier_coefficients"] if pos_enc == "fourier" else []) + \
+        [f"early_pts_layers.{2 * i}.{w}" for i in range(L + 1) for w in ("weight", "bias")] + ["output_linear.0.weight", "output_linear.0.bias"]
+    gref = np.concatenate([params[k].grad.numpy().reshape(-1) for k in order])
+    got = tr.grad.cpu().numpy()
+    assert np.max(np.abs(got - gref)) <= 1e-4 * np.abs(gref).max(), np.max(np.abs(got - gref)) / np.abs(gref).max()
+    # parameters after Adam: wherever the gradient is well above Adam's eps the update is -lr*sign(g) on both sides
+    sd = model.state_dict()
+    for k in order:
+        g = params[k].grad.numpy()
+        big = np.abs(g) > 1e-5
+        assert np.allclose(sd[k].cpu().numpy()[big], params[k].detach().numpy()[big], rtol=0, atol=2e-6), k
