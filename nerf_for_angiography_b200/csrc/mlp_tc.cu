@@ -1,28 +1,36 @@
-// mlp_tc.cu -- the fused CPPN MLP on Blackwell tensor cores (ANGIO_PREC_BF16): Fourier positional encoding fused
-// into the first layer, every layer's weights resident in shared memory, activations never leave the SM.
+// mlp_tc.cu -- the fused CPPN MLP on Blackwell tensor cores (ANGIO_PREC_BF16): forward, data-gradient chain and
+// weight gradients as three hand-written tcgen05 kernels.  Fourier positional encoding is fused into the first layer,
+// every layer's weights stay resident in shared memory, activations travel TMEM -> registers -> TMEM and never touch
+// shared or global memory on the inference path.
 // Replaces CPPN.forward (/root/reference/model/CPPN.py:166-222), the chunk loop of get_predictions
-// (/root/reference/nerf/nerf_helpers.py:24-45), the midpoint gather (/root/reference/nerf/run_nerf_acc.py:290-292)
-// and, through the fused output transforms, the alpha_fn / occ_eval_fn closures
-// (/root/reference/nerf/nerf_helpers_acc.py:11-25,66-70).
+// (/root/reference/nerf/nerf_helpers.py:24-45), the midpoint gather (/root/reference/nerf/run_nerf_acc.py:290-292), the
+// alpha_fn / occ_eval_fn closures (/root/reference/nerf/nerf_helpers_acc.py:11-25,66-70) and torch autograd through the MLP
+// (/root/reference/nerf/run_nerf_acc.py:306).
 //
-// Kernel shape (width 128; one persistent CTA per SM, 288 threads = 9 warps):
-//   warp 0      : loads the packed bf16 weight image once with 1-D bulk async copies (TMA unit), then issues every
-//                 tcgen05.mma (one elected lane).
-//   warps 1-4   : "group 0", warps 5-8: "group 1".  Each group owns one 128-sample tile slot: thread r <-> sample
-//                 row r <-> TMEM lane r.  A group computes the encoded features of its tile, stores them as bf16
-//                 into TMEM (tcgen05.st), and after each layer's MMA pulls the fp32 accumulators back
-//                 (tcgen05.ld), adds the bias, applies ReLU, re-packs to bf16 and feeds them straight back into
-//                 TMEM as the next layer's A operand.  The last hidden layer is reduced against w_out on CUDA cores.
-//   Two slots ping-pong: while group 0 runs the epilogue of layer l, the tensor core runs layer l of group 1's tile.
+// Notation: a_0 = encoded features (K padded to 64), a_1..a_{L+1} = hidden activations (width 128, post-ReLU),
+//           linear layer w: z_{w+1} = W_w a_w + b_w,  delta_d = dLoss/dz_d,  logit = w_out . a_{L+1} + b_out.
 //
-//   D[128 x 128] (TMEM, fp32) = A[128 x K] (TMEM, bf16, K-major)  x  W_l[128 x K]^T (SMEM, bf16, SWIZZLE_128B)
+// (1) mlp_fwd_tc_kernel   one persistent CTA per SM, 288 threads:
+//       warp 0     loads the packed bf16 weight image once (1-D bulk async copies on the TMA unit), then issues every
+//                  tcgen05.mma from one lane;
+//       warps 1-4 / 5-8  two "tile groups": thread r <-> sample row r <-> TMEM lane r of the group's 128-sample tile.
+//                  A group encodes its samples, stores the bf16 features into TMEM (tcgen05.st) as the A operand, and
+//                  after each layer's MMA pulls the fp32 accumulators back (tcgen05.ld), adds the bias (packed
+//                  f32x2), applies ReLU while packing to bf16 and stores them straight back into TMEM as the next A.
+//                  The output layer is one more MMA with N = 16.  The two groups ping-pong so the tensor core runs
+//                  one tile while the other tile is in its epilogue.
+//       D[128 x N] (TMEM fp32) = A[128 x K] (TMEM bf16, K-major) x W[N x K]^T (SMEM bf16, SWIZZLE_128B)
+//       Training variant: every a_d row is also written to HBM as a ready-to-MMA swizzled tile image.
+// (2) mlp_dgrad_tc_kernel same structure, running the chain delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}) with the
+//       SAME resident weight image read through an MN-major descriptor; writes the delta tile images and accumulates the
+//       Fourier-coefficient gradient (the coefficients are learned, model/CPPN.py:73-75).
+// (3) mlp_wgrad_tc_kernel dW_w = delta_{w+1}^T a_w (reduction over samples): tile images stream through a 3-stage
+//       bulk-copy ring, both operands MN-major, fp32 accumulators stay in TMEM for the CTA's whole tile range; bias
+//       gradients ride along as an N = 16 MMA against a tile of ones; a fixed-order reduction over CTAs follows.
 //
-// TMEM map (512 columns allocated): accumulators slot s at columns [128 s, 128 s + 128); A operand slot s at columns
-// [256 + 64 s, 256 + 64 s + 64) (two bf16 per 32-bit column).
 // First-layer K layout: [x_hi(3) x_lo(3) (sin_j, cos_j) x 3L, 0-pad] -- world coordinates reach +-173 and bf16 keeps 8
-// bits, so x is fed as a hi/lo bf16 pair against duplicated weight columns.  The phase a = fl(fl(2 pi x) c) is
-// computed exactly as the reference does in fp32, reduced by 2 pi with a two-constant Cody-Waite step, then
-// sin/cos use the SFU (abs err ~1e-6, far below bf16 resolution).
+// bits, so x enters as a hi/lo bf16 pair against duplicated weight columns.  The phase a = fl(fl(2 pi x) c) is computed
+// exactly as the reference does in fp32, reduced by 2 pi with a two-constant Cody-Waite step, then sin/cos use the SFU.
 #include "mlp_layout.cuh"
 #include "tc05.cuh"
 
@@ -31,23 +39,26 @@ namespace {
 using angio::MlpLayout;
 using namespace tc05;
 
-constexpr int kH = 128;            // hidden width handled by this kernel
+constexpr int kH = 128;            // hidden width handled by these kernels
 constexpr int kTile = 128;         // samples per tile (UMMA M)
 constexpr int kThreads = 288;      // warp 0 = control/MMA, warps 1-4 / 5-8 = tile groups
 constexpr int kTmemCols = 512;
 constexpr float kTwoPi = 6.2831855f;
+constexpr int kA0Bytes = 16384;    // a_0 tile image: [128 rows x 64 cols] bf16
+constexpr int kActBytes = 32768;   // a_d / delta_d tile image: two [128 x 64] blocks
 
 struct TcPlan {
-  int n_hidden;     // number of 128x128 layers
-  int basis;        // Fourier basis L (0 = no encoding)
-  int k0;           // true first-layer K: 6 + 6 L
+  int n_hidden;     // L: number of 128x128 layers
+  int basis;        // Fourier basis (0 = no encoding)
+  int k0;           // true first-layer K: 6 + 6 * basis
   int k0_pad;       // rounded up to 16
-  int off_const;    // byte offset of the fp32 constant block inside the packed image
+  int off_wout;     // byte offset of the output-layer block ([16 x 128] bf16, row 0 = w_out)
+  int off_const;    // byte offset of the fp32 constant block
   int n_const;      // floats in the constant block
   int total_bytes;  // packed image size (multiple of 16)
 };
 
-__host__ __device__ inline int w_offset(int l) { return l == 0 ? 0 : 16384 + (l - 1) * 32768; }
+__host__ __device__ inline int w_offset(int w) { return w == 0 ? 0 : 16384 + (w - 1) * 32768; }
 
 inline bool make_plan(const MlpLayout& L, TcPlan* p) {
   if (L.H != kH) return false;
@@ -56,8 +67,9 @@ inline bool make_plan(const MlpLayout& L, TcPlan* p) {
   p->k0 = 6 + 6 * L.basis;
   p->k0_pad = (p->k0 + 15) / 16 * 16;
   if (p->k0_pad > 64) return false;
-  p->off_const = 16384 + L.n_hidden * 32768;
-  // biases (n_hidden+1) x 128 | w_out 128 | b_out (padded to 4) | coef (padded to 4)
+  p->off_wout = 16384 + L.n_hidden * 32768;
+  p->off_const = p->off_wout + 4096;
+  // biases (L+1) x 128 | w_out 128 | b_out (padded to 4) | coef (padded to 4)
   p->n_const = (L.n_hidden + 2) * 128 + 4 + (3 * L.basis + 3) / 4 * 4;
   p->total_bytes = (p->off_const + p->n_const * 4 + 15) / 16 * 16;
   return p->total_bytes + 2048 <= 227 * 1024;
@@ -65,7 +77,7 @@ inline bool make_plan(const MlpLayout& L, TcPlan* p) {
 
 // ------------------------------------------------------------------------------------------------ weight packing
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ params, MlpLayout L, TcPlan P, uint8_t* __restrict__ out) {
-  const int n_w_elems = (16384 + P.n_hidden * 32768) / 2;
+  const int n_w_elems = (16384 + P.n_hidden * 32768 + 4096) / 2;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid < n_w_elems) {
     float v = 0.0f;
@@ -79,12 +91,17 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
         v = params[L.off_w[0] + (int64_t)n * L.d_in + src];
       }
       byte_off = sw128_offset(n, k);
-    } else {
+    } else if (tid < 8192 + P.n_hidden * 16384) {
       const int e = tid - 8192;
-      const int l = 1 + e / 16384, r = e % 16384;
+      const int w = 1 + e / 16384, r = e % 16384;
       const int n = r / 128, k = r % 128;
-      v = params[L.off_w[l] + (int64_t)n * kH + k];
-      byte_off = w_offset(l) + (k / 64) * 16384 + sw128_offset(n, k % 64);
+      v = params[L.off_w[w] + (int64_t)n * kH + k];
+      byte_off = w_offset(w) + (k / 64) * 16384 + sw128_offset(n, k % 64);
+    } else {  // output layer block: [16 n][128 k], two K blocks of 2 KB; row 0 = w_out
+      const int e = tid - 8192 - P.n_hidden * 16384;
+      const int n = e / 128, k = e % 128;
+      if (n == 0) v = params[L.off_w[L.n_linear - 1] + k];
+      byte_off = P.off_wout + (k / 64) * 2048 + sw128_offset(n, k % 64);
     }
     *reinterpret_cast<__nv_bfloat16*>(out + byte_off) = __float2bfloat16_rn(v);
   }
@@ -99,8 +116,8 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
   }
 }
 
-// ------------------------------------------------------------------------------------------------ forward kernel
-struct __align__(8) FwdBarriers {
+// ------------------------------------------------------------------------------------------------ shared device pieces
+struct __align__(8) PipeBarriers {
   uint64_t w_ready;
   uint64_t a_ready[2];
   uint64_t acc_ready[2];
@@ -124,17 +141,60 @@ __device__ __forceinline__ float out_transform(float logit, float dt) {
   return 1.0f - __expf(-s * dt);
 }
 
-template <int OUT_MODE>
-__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
-                                                                 float* __restrict__ out) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ FwdBarriers bars;
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int64_t n = in.n;
-  const int64_t n_tiles = (n + kTile - 1) / kTile;
-  // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...; slot = j & 1
-  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+// encoded features of one sample as 32 bf16x2 words (K = 64): every index is static
+__device__ __forceinline__ void encode_features(const float x[3], const float* __restrict__ coef, int nb, uint32_t (&pk)[32]) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) pk[c] = 0u;
+  float hi[3], lo[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    hi[c] = __bfloat162float(__float2bfloat16_rn(x[c]));
+    lo[c] = x[c] - hi[c];
+  }
+  pk[0] = pack_bf16x2(hi[0], hi[1]);
+  pk[1] = pack_bf16x2(hi[2], lo[0]);
+  pk[2] = pack_bf16x2(lo[1], lo[2]);
+#pragma unroll
+  for (int jf = 0; jf < 29; ++jf) {  // up to 29 (sin, cos) pairs fit k0_pad <= 64
+    if (jf < nb) {
+      const float a = __fmul_rn(__fmul_rn(kTwoPi, x[jf % 3]), coef[jf]);
+      float sn, cs;
+      sincos_reduced(a, sn, cs);
+      pk[3 + jf] = pack_bf16x2(sn, cs);
+    }
+  }
+}
 
+// store one 64-column half (32 bf16x2 words = eight 16-byte chunks) of row `row` into a swizzled tile-image block
+__device__ __forceinline__ void store_row_block(uint8_t* __restrict__ block, int row, const uint32_t (&pk)[32]) {
+  uint8_t* base = block + row * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 v = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    *reinterpret_cast<uint4*>(base + ((c ^ (row & 7)) << 4)) = v;
+  }
+}
+__device__ __forceinline__ void load_row_block(const uint8_t* __restrict__ block, int row, uint32_t (&pk)[32]) {
+  const uint8_t* base = block + row * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + ((c ^ (row & 7)) << 4)));
+    pk[4 * c] = v.x; pk[4 * c + 1] = v.y; pk[4 * c + 2] = v.z; pk[4 * c + 3] = v.w;
+  }
+}
+
+// bf16x2 word -> bf16x2 mask (1.0 where the element is non-zero)
+__device__ __forceinline__ uint32_t relu_mask2(uint32_t a2) {
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&a2);
+  const __nv_bfloat162 m = __hne2(a, __float2bfloat162_rn(0.0f));
+  return *reinterpret_cast<const uint32_t*>(&m);
+}
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a2, uint32_t b2) {
+  const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a2), *reinterpret_cast<const __nv_bfloat162*>(&b2));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+__device__ __forceinline__ void pipe_setup(PipeBarriers& bars, int warp) {
   if (threadIdx.x == 0) {
     mbar_init(&bars.w_ready, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(&bars.a_ready[s], 128); mbar_init(&bars.acc_ready[s], 1); }
@@ -144,38 +204,61 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+}
+
+__device__ __forceinline__ void load_weight_image(uint8_t* smem, const uint8_t* __restrict__ packed, int total_bytes, uint64_t* bar) {
+  mbar_arrive_expect_tx(bar, (uint32_t)total_bytes);
+  for (int off = 0; off < total_bytes; off += 32768) {
+    const int bytes = (total_bytes - off < 32768) ? total_bytes - off : 32768;
+    bulk_g2s(smem + off, packed + off, (uint32_t)bytes, bar);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ (1) forward
+// saved (TRAIN): [a_0 images: n_tiles x 16 KB][a_1 images: n_tiles x 32 KB] ... [a_{L+1} images]
+template <int OUT_MODE, bool TRAIN>
+__global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
+                                                                 float* __restrict__ out, uint8_t* __restrict__ saved) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ PipeBarriers bars;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t n = in.n;
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...; slot = j & 1
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  pipe_setup(bars, warp);
   const uint32_t tmem = bars.tmem_base;
   const float* consts = reinterpret_cast<const float*>(smem + P.off_const);
-  const int L1 = P.n_hidden + 1;  // number of MMA layers
+  const int n_stages = P.n_hidden + 2;  // L+1 layers with N = 128, then the output layer with N = 16
 
   if (warp == 0) {
     // ===================== control warp: weight load, then MMA issue =====================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&bars.w_ready, (uint32_t)P.total_bytes);
-      for (int off = 0; off < P.total_bytes; off += 32768) {
-        const int bytes = (P.total_bytes - off < 32768) ? P.total_bytes - off : 32768;
-        bulk_g2s(smem + off, packed + off, (uint32_t)bytes, &bars.w_ready);
-      }
-    }
+    if (lane == 0) load_weight_image(smem, packed, P.total_bytes, &bars.w_ready);
     mbar_wait(&bars.w_ready, 0);
     const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 0);
+    const uint32_t idesc_out = make_idesc_bf16(kTile, 16, 0, 0);
     const uint32_t smem_base = smem_u32(smem);
     uint32_t phase[2] = {0, 0};
     for (int64_t j0 = 0; j0 < my_tiles; j0 += 2) {
       const int n_slots = (my_tiles - j0 >= 2) ? 2 : 1;
-      for (int l = 0; l < L1; ++l) {
+      for (int st = 0; st < n_stages; ++st) {
         for (int s = 0; s < n_slots; ++s) {
           mbar_wait(&bars.a_ready[s], phase[s]);
           phase[s] ^= 1;
           fence_after_sync();
           if (lane == 0) {
-            const uint32_t d_tmem = tmem + s * 128;
             const uint32_t a_tmem = tmem + 256 + s * 64;
-            const int ksteps = (l == 0) ? P.k0_pad / 16 : kH / 16;
-            const uint32_t wbase = smem_base + w_offset(l);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint64_t db = make_smem_desc_sw128(wbase + (k / 4) * 16384 + (k % 4) * 32, 16, 1024);
-              mma_ts(d_tmem, a_tmem + k * 8, db, idesc, k > 0);
+            if (st < n_stages - 1) {
+              const uint32_t d_tmem = tmem + s * 128;
+              const int ksteps = (st == 0) ? P.k0_pad / 16 : kH / 16;
+              const uint32_t wbase = smem_base + w_offset(st);
+              for (int k = 0; k < ksteps; ++k)
+                mma_ts(d_tmem, a_tmem + k * 8, make_smem_desc_sw128(wbase + (k / 4) * 16384 + (k % 4) * 32, 16, 1024), idesc, k > 0);
+            } else {
+              const uint32_t d_tmem = tmem + 384 + s * 16;
+              const uint32_t wbase = smem_base + P.off_wout;
+              for (int k = 0; k < kH / 16; ++k)
+                mma_ts(d_tmem, a_tmem + k * 8, make_smem_desc_sw128(wbase + (k / 4) * 2048 + (k % 4) * 32, 16, 1024), idesc_out, k > 0);
             }
             mma_commit(&bars.acc_ready[s]);
           }
@@ -191,9 +274,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t acc_tmem = tmem + g * 128 + lane_off;
     const uint32_t a_tmem = tmem + 256 + g * 64 + lane_off;
+    const uint32_t oacc_tmem = tmem + 384 + g * 16 + lane_off;
     mbar_wait(&bars.w_ready, 0);                  // biases / coefficients live in the packed image
     const float* coef = consts + (P.n_hidden + 2) * 128 + 4;
-    const float* w_out = consts + (P.n_hidden + 1) * 128;
     const float b_out = consts[(P.n_hidden + 2) * 128];
     const int nb = 3 * P.basis;
     uint32_t phase = 0;
@@ -201,7 +284,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
       const int64_t tile = blockIdx.x + j * gridDim.x;
       const int64_t i = tile * kTile + row;
       const bool valid = i < n;
-      // ---- sample position (reference op order) and encoded features -> TMEM A operand
       float x[3] = {0.f, 0.f, 0.f};
       float dt = 0.f;
       if (valid) {
@@ -209,28 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         if (OUT_MODE == ANGIO_OUT_ALPHA) dt = in.t_ends[i] - in.t_starts[i];
       }
       {
-        // K layout: [x_hi(3) x_lo(3) | (sin_j, cos_j) pairs | 0-pad]; every index below is static
         uint32_t pk[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) pk[c] = 0u;
-        float hi[3], lo[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          hi[c] = __bfloat162float(__float2bfloat16_rn(x[c]));
-          lo[c] = x[c] - hi[c];
-        }
-        pk[0] = pack_bf16x2(hi[0], hi[1]);
-        pk[1] = pack_bf16x2(hi[2], lo[0]);
-        pk[2] = pack_bf16x2(lo[1], lo[2]);
-#pragma unroll
-        for (int jf = 0; jf < 29; ++jf) {      // up to 29 (sin, cos) pairs fit k0_pad <= 64
-          if (jf < nb) {
-            const float a = __fmul_rn(__fmul_rn(kTwoPi, x[jf % 3]), coef[jf]);
-            float sn, cs;
-            sincos_reduced(a, sn, cs);
-            pk[3 + jf] = pack_bf16x2(sn, cs);
-          }
-        }
+        encode_features(x, coef, nb, pk);
         uint32_t v16[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) v16[c] = pk[c];
@@ -240,50 +302,406 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
           for (int c = 0; c < 16; ++c) v16[c] = pk[16 + c];
           tmem_st16(a_tmem + 16, v16);
         }
+        if (TRAIN) store_row_block(saved + tile * kA0Bytes, row, pk);
       }
       wait_st();
       fence_before_sync();
       mbar_arrive(&bars.a_ready[g]);
-      // ---- layers
-      float dot = 0.0f;
-      for (int l = 0; l < L1; ++l) {
+      // ---- hidden layers: acc + bias -> relu -> bf16 -> next A operand
+      for (int l = 0; l <= P.n_hidden; ++l) {
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
         const float* bias = consts + l * 128;
-        const bool last = (l == L1 - 1);
+        uint8_t* img = TRAIN ? saved + n_tiles * kA0Bytes + ((int64_t)l * n_tiles + tile) * kActBytes : nullptr;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kH; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(acc_tmem + c0, r);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(acc_tmem + half * 64, r0);
+          tmem_ld32(acc_tmem + half * 64 + 32, r1);
           wait_ld();
-          if (!last) {
-            uint32_t v16[16];
+          uint32_t pk[32];
 #pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const float2 b2 = *reinterpret_cast<const float2*>(bias + c0 + 2 * jj);
-              v16[jj] = pack_bf16x2_relu(__uint_as_float(r[2 * jj]) + b2.x, __uint_as_float(r[2 * jj + 1]) + b2.y);
-            }
-            tmem_st16(a_tmem + c0 / 2, v16);
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              dot = fmaf(fmaxf(__uint_as_float(r[jj]) + bias[c0 + jj], 0.0f), w_out[c0 + jj], dot);
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + half * 64 + 4 * jj);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + half * 64 + 32 + 4 * jj);
+            const float2 u0 = __fadd2_rn(make_float2(__uint_as_float(r0[4 * jj]), __uint_as_float(r0[4 * jj + 1])), make_float2(b0.x, b0.y));
+            const float2 u1 = __fadd2_rn(make_float2(__uint_as_float(r0[4 * jj + 2]), __uint_as_float(r0[4 * jj + 3])), make_float2(b0.z, b0.w));
+            const float2 u2 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * jj]), __uint_as_float(r1[4 * jj + 1])), make_float2(b1.x, b1.y));
+            const float2 u3 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * jj + 2]), __uint_as_float(r1[4 * jj + 3])), make_float2(b1.z, b1.w));
+            pk[2 * jj] = pack_bf16x2_relu(u0.x, u0.y);
+            pk[2 * jj + 1] = pack_bf16x2_relu(u1.x, u1.y);
+            pk[16 + 2 * jj] = pack_bf16x2_relu(u2.x, u2.y);
+            pk[16 + 2 * jj + 1] = pack_bf16x2_relu(u3.x, u3.y);
           }
+          tmem_st32(a_tmem + half * 32, pk);
+          if (TRAIN) store_row_block(img + half * 16384, row, pk);
         }
-        if (!last) {
-          wait_st();
-          fence_before_sync();
-          mbar_arrive(&bars.a_ready[g]);
-        }
+        wait_st();
+        fence_before_sync();
+        mbar_arrive(&bars.a_ready[g]);
       }
-      if (valid) out[i] = out_transform<OUT_MODE>(dot + b_out, dt);
+      // ---- output layer accumulator: column 0 of the N = 16 MMA
+      mbar_wait(&bars.acc_ready[g], phase);
+      phase ^= 1;
+      fence_after_sync();
+      uint32_t o;
+      tmem_ld1(oacc_tmem, o);
+      wait_ld();
+      if (valid) out[i] = out_transform<OUT_MODE>(__uint_as_float(o) + b_out, dt);
     }
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
+
+// ------------------------------------------------------------------------------------------------ (2) data-gradient chain
+// delta images out: [delta_1: n_tiles x 32 KB] ... [delta_{L+1}]; coef_partials: [gridDim.x][32] floats
+__global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
+                                                                   const uint8_t* __restrict__ saved, const float* __restrict__ grad_out,
+                                                                   uint8_t* __restrict__ delta, float* __restrict__ coef_partials) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ PipeBarriers bars;
+  __shared__ float s_coef[8][32];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t n = in.n;
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  pipe_setup(bars, warp);
+  const uint32_t tmem = bars.tmem_base;
+  const float* consts = reinterpret_cast<const float*>(smem + P.off_const);
+  const int L = P.n_hidden;
+  const bool enc = P.basis > 0;
+  const int n_stages = L + (enc ? 1 : 0);   // stage st consumes delta_{L+1-st} and multiplies by W_{L-st}
+  const int nb = 3 * P.basis;
+  float dcoef[29];
+#pragma unroll
+  for (int jf = 0; jf < 29; ++jf) dcoef[jf] = 0.0f;
+
+  if (warp == 0) {
+    if (lane == 0) load_weight_image(smem, packed, P.total_bytes, &bars.w_ready);
+    mbar_wait(&bars.w_ready, 0);
+    // B = W_w read through an MN-major descriptor: rows = out features (K), in features contiguous (N)
+    const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 1);
+    const uint32_t idesc0 = make_idesc_bf16(kTile, 64, 0, 1);
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t phase[2] = {0, 0};
+    for (int64_t j0 = 0; j0 < my_tiles && n_stages > 0; j0 += 2) {
+      const int n_slots = (my_tiles - j0 >= 2) ? 2 : 1;
+      for (int st = 0; st < n_stages; ++st) {
+        const int w = L - st;  // weight index
+        for (int s = 0; s < n_slots; ++s) {
+          mbar_wait(&bars.a_ready[s], phase[s]);
+          phase[s] ^= 1;
+          fence_after_sync();
+          if (lane == 0) {
+            const uint32_t d_tmem = tmem + s * 128;
+            const uint32_t a_tmem = tmem + 256 + s * 64;
+            const uint32_t wbase = smem_base + w_offset(w);
+            for (int k = 0; k < kH / 16; ++k)
+              mma_ts(d_tmem, a_tmem + k * 8, make_smem_desc_sw128(wbase + k * 2048, 16384, 1024), w == 0 ? idesc0 : idesc, k > 0);
+            mma_commit(&bars.acc_ready[s]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int g = (warp - 1) / 4;
+    const int q = warp % 4;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t acc_tmem = tmem + g * 128 + lane_off;
+    const uint32_t a_tmem = tmem + 256 + g * 64 + lane_off;
+    mbar_wait(&bars.w_ready, 0);
+    const float* coef = consts + (L + 2) * 128 + 4;
+    const float* w_out = consts + (L + 1) * 128;
+    const uint8_t* act_base = saved + n_tiles * kA0Bytes;   // a_d image of tile t: act_base + ((d-1) * n_tiles + t) * 32 KB
+    uint32_t phase = 0;
+    for (int64_t j = g; j < my_tiles; j += 2) {
+      const int64_t tile = blockIdx.x + j * gridDim.x;
+      const int64_t i = tile * kTile + row;
+      const bool valid = i < n;
+      const float gr = valid ? grad_out[i] : 0.0f;
+      // ---- delta_{L+1} = g * w_out * relu'(a_{L+1})
+      {
+        const uint8_t* a_img = act_base + ((int64_t)L * n_tiles + tile) * kActBytes;
+        uint8_t* d_img = delta + ((int64_t)L * n_tiles + tile) * kActBytes;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t a[32], pk[32];
+          load_row_block(a_img + half * 16384, row, a);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float2 w2 = *reinterpret_cast<const float2*>(w_out + half * 64 + 2 * c);
+            pk[c] = hmul2_u32(pack_bf16x2(gr * w2.x, gr * w2.y), relu_mask2(a[c]));
+          }
+          tmem_st32(a_tmem + half * 32, pk);
+          store_row_block(d_img + half * 16384, row, pk);
+        }
+      }
+      if (n_stages > 0) {
+        wait_st();
+        fence_before_sync();
+        mbar_arrive(&bars.a_ready[g]);
+      }
+      // ---- hidden chain: delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}),  d = L+1 .. 2
+      for (int st = 0; st < L; ++st) {
+        const int d = L + 1 - st;            // consumed delta index; produces delta_{d-1}
+        mbar_wait(&bars.acc_ready[g], phase);
+        phase ^= 1;
+        fence_after_sync();
+        const uint8_t* a_img = act_base + ((int64_t)(d - 2) * n_tiles + tile) * kActBytes;   // a_{d-1}
+        uint8_t* d_img = delta + ((int64_t)(d - 2) * n_tiles + tile) * kActBytes;            // delta_{d-1}
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r0[32], r1[32], a[32], pk[32];
+          tmem_ld32(acc_tmem + half * 64, r0);
+          tmem_ld32(acc_tmem + half * 64 + 32, r1);
+          load_row_block(a_img + half * 16384, row, a);
+          wait_ld();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            pk[c] = hmul2_u32(pack_bf16x2(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])), relu_mask2(a[c]));
+            pk[16 + c] = hmul2_u32(pack_bf16x2(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])), relu_mask2(a[16 + c]));
+          }
+          tmem_st32(a_tmem + half * 32, pk);
+          store_row_block(d_img + half * 16384, row, pk);
+        }
+        if (st + 1 < n_stages) {
+          wait_st();
+          fence_before_sync();
+          mbar_arrive(&bars.a_ready[g]);
+        }
+      }
+      // ---- feature gradient (delta_1 W_0) -> Fourier-coefficient gradient
+      if (enc) {
+        mbar_wait(&bars.acc_ready[g], phase);
+        phase ^= 1;
+        fence_after_sync();
+        uint32_t r0[32], r1[32];
+        tmem_ld32(acc_tmem, r0);
+        tmem_ld32(acc_tmem + 32, r1);
+        wait_ld();
+        if (valid) {
+          float x[3];
+          angio::sample_position(in, i, x);
+#pragma unroll
+          for (int jf = 0; jf < 29; ++jf) {
+            if (jf < nb) {
+              const float tp = __fmul_rn(kTwoPi, x[jf % 3]);
+              float sn, cs;
+              sincos_reduced(__fmul_rn(tp, coef[jf]), sn, cs);
+              // feature columns 6+2j (sin) and 7+2j (cos); d sin/d coef = cos * 2 pi x, d cos/d coef = -sin * 2 pi x
+              const int ks = 6 + 2 * jf, kc = 7 + 2 * jf;
+              const float ds = __uint_as_float(ks < 32 ? r0[ks & 31] : r1[ks & 31]);
+              const float dc = __uint_as_float(kc < 32 ? r0[kc & 31] : r1[kc & 31]);
+              dcoef[jf] = fmaf(ds * cs - dc * sn, tp, dcoef[jf]);
+            }
+          }
+        }
+      }
+    }
+    // ---- per-CTA reduction of the coefficient gradient (fixed order)
+    if (enc) {
+#pragma unroll
+      for (int jf = 0; jf < 29; ++jf) {
+        if (jf < nb) {
+          float v = dcoef[jf];
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+          if (lane == 0) s_coef[warp - 1][jf] = v;
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tmem_dealloc(tmem, kTmemCols);
+    if (enc && lane < nb) {
+      float v = 0.0f;
+      for (int wv = 0; wv < 8; ++wv) v += s_coef[wv][lane];
+      coef_partials[blockIdx.x * 32 + lane] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ (3) weight gradients
+// grid = (L+1) * G CTAs; CTA (d-1, j) accumulates dW_{d-1} = delta_d^T a_{d-1} and db_{d-1} over tiles j, j+G, ...
+// partials: [gridDim.x][128 * 128 + 128] floats
+constexpr int kWgStages = 3;
+constexpr int kWgThreads = 128;
+constexpr int kWgPartial = 128 * 128 + 128;
+
+struct __align__(8) WgBarriers {
+  uint64_t full[kWgStages];
+  uint64_t empty[kWgStages];
+  uint64_t done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ delta,
+                                                                     int64_t n_tiles, int L, int G, float* __restrict__ partials) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ WgBarriers bars;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int d = blockIdx.x / G + 1;                   // delta index 1..L+1
+  const int j0 = blockIdx.x % G;
+  const int n_in = (d == 1) ? 64 : 128;               // columns of a_{d-1}
+  const uint32_t b_bytes = (d == 1) ? kA0Bytes : kActBytes;
+  uint8_t* s_ones = smem;                             // 4 KB of bf16 1.0
+  uint8_t* s_stage = smem + 4096;                     // kWgStages x (32 KB delta + 32 KB act)
+  for (int t = threadIdx.x; t < 1024; t += kWgThreads) reinterpret_cast<uint32_t*>(s_ones)[t] = 0x3F803F80u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
+    mbar_init(&bars.done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&bars.tmem_base, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bars.tmem_base;
+  const int64_t my_tiles = (n_tiles > j0) ? (n_tiles - j0 + G - 1) / G : 0;
+  const uint8_t* d_base = delta + (int64_t)(d - 1) * n_tiles * kActBytes;
+  const uint8_t* a_base = (d == 1) ? saved : saved + n_tiles * kA0Bytes + (int64_t)(d - 2) * n_tiles * kActBytes;
+
+  if (warp == 0 && lane == 0) {
+    // ---- producer: bulk-copy the (delta_d, a_{d-1}) tile images into the ring
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int s = (int)(t % kWgStages);
+      const uint32_t ph = (uint32_t)((t / kWgStages) & 1);
+      mbar_wait(&bars.empty[s], ph ^ 1);
+      const int64_t tile = j0 + t * G;
+      mbar_arrive_expect_tx(&bars.full[s], kActBytes + b_bytes);
+      bulk_g2s(s_stage + s * 65536, d_base + tile * kActBytes, kActBytes, &bars.full[s]);
+      bulk_g2s(s_stage + s * 65536 + 32768, a_base + tile * (int64_t)b_bytes, b_bytes, &bars.full[s]);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer: D[out x in] += delta^T a (both MN-major), Db[out x 16] += delta^T ones
+    const uint32_t idesc_w = make_idesc_bf16(128, n_in, 1, 1);
+    const uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 0);
+    const uint32_t ones = smem_u32(s_ones);
+    for (int64_t t = 0; t < my_tiles; ++t) {
+      const int s = (int)(t % kWgStages);
+      const uint32_t ph = (uint32_t)((t / kWgStages) & 1);
+      mbar_wait(&bars.full[s], ph);
+      fence_after_sync();
+      const uint32_t da = smem_u32(s_stage + s * 65536), ba = da + 32768;
+      for (int k = 0; k < kTile / 16; ++k) {
+        const uint64_t desc_a = make_smem_desc_sw128(da + k * 2048, 16384, 1024);
+        mma_ss(tmem, desc_a, make_smem_desc_sw128(ba + k * 2048, 16384, 1024), idesc_w, (t | k) != 0);
+        mma_ss(tmem + 128, desc_a, make_smem_desc_sw128(ones + (k / 4) * 2048 + (k % 4) * 32, 16, 1024), idesc_b, (t | k) != 0);
+      }
+      mma_commit(&bars.empty[s]);
+    }
+    mma_commit(&bars.done);
+  }
+  __syncwarp();
+  mbar_wait(&bars.done, 0);
+  fence_after_sync();
+  // ---- dump the accumulators: thread r holds row r (out feature) of dW and db[r]
+  {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float* Pp = partials + (int64_t)blockIdx.x * kWgPartial;
+    if (my_tiles > 0) {
+      for (int c0 = 0; c0 < n_in; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_off + c0, r);
+        wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          *reinterpret_cast<float4*>(Pp + row * 128 + c0 + c) =
+              make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+      }
+      uint32_t b;
+      tmem_ld1(tmem + lane_off + 128, b);
+      wait_ld();
+      Pp[128 * 128 + row] = __uint_as_float(b);
+    } else {
+      for (int c = 0; c < n_in; ++c) Pp[row * 128 + c] = 0.0f;
+      Pp[128 * 128 + row] = 0.0f;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+// fixed-order reduction over the G CTAs of each layer, scattered into the reference parameter layout
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int G, MlpLayout Lay, TcPlan P,
+                                                           float* __restrict__ grad) {
+  const int w = blockIdx.y;                                 // linear layer 0..L
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;      // element of [128 x 128] (+128 bias)
+  if (e >= kWgPartial) return;
+  if (w == 0 && e < 128 * 128 && (e % 128) >= 64) return;   // layer 0 accumulates only 64 feature columns
+  float acc = 0.0f;
+  for (int gidx = 0; gidx < G; ++gidx) acc += partials[((int64_t)w * G + gidx) * kWgPartial + e];
+  if (e >= 128 * 128) { grad[Lay.off_b[w] + (e - 128 * 128)] = acc; return; }
+  const int o = e / 128, c = e % 128;
+  if (w > 0) { grad[Lay.off_w[w] + (int64_t)o * 128 + c] = acc; return; }
+  // layer 0: feature column c -> reference column; x_hi and x_lo both belong to column c % 3
+  if (c >= P.k0) return;
+  if (c < 3) {
+    float lo = 0.0f;
+    for (int gidx = 0; gidx < G; ++gidx) lo += partials[((int64_t)gidx) * kWgPartial + o * 128 + c + 3];
+    grad[Lay.off_w[0] + (int64_t)o * Lay.d_in + c] = acc + lo;
+  } else if (c >= 6) {
+    const int jj = (c - 6) / 2;
+    const int src = ((c - 6) & 1) ? 3 + 3 * P.basis + jj : 3 + jj;
+    grad[Lay.off_w[0] + (int64_t)o * Lay.d_in + src] = acc;
+  }
+}
+
+// output layer: dw_out[o] = sum_s g[s] a_{L+1}[s][o], db_out = sum_s g[s]; one warp per tile, block partials
+__global__ void __launch_bounds__(256) outgrad_partial_kernel(const uint8_t* __restrict__ a_last, const float* __restrict__ g, int64_t n,
+                                                              int64_t n_tiles, float* __restrict__ partials /*[gridDim.x][132]*/) {
+  __shared__ float s_acc[8][132];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float gsum = 0.0f;
+  for (int64_t tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+    const uint8_t* img = a_last + tile * kActBytes;
+    for (int r = 0; r < kTile; ++r) {
+      const int64_t i = tile * kTile + r;
+      if (i >= n) break;
+      const float gv = g[i];
+      // lane handles columns 4*lane .. 4*lane+3 (8 bytes inside the swizzled row)
+      const int col = 4 * lane;
+      const uint8_t* p = img + (col / 64) * 16384 + sw128_offset(r, col % 64);
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+      const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+      const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+      acc[0] = fmaf(gv, f0.x, acc[0]); acc[1] = fmaf(gv, f0.y, acc[1]);
+      acc[2] = fmaf(gv, f1.x, acc[2]); acc[3] = fmaf(gv, f1.y, acc[3]);
+      if (lane == 0) gsum += gv;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) s_acc[warp][4 * lane + c] = acc[c];
+  if (lane == 0) s_acc[warp][128] = gsum;
+  __syncthreads();
+  if (threadIdx.x < 129) {
+    float v = 0.0f;
+    for (int wv = 0; wv < 8; ++wv) v += s_acc[wv][threadIdx.x];
+    partials[(int64_t)blockIdx.x * 132 + threadIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(256) small_reduce_kernel(const float* __restrict__ partials, int n_part, int stride, int len,
+                                                           float* __restrict__ out0, int split, float* __restrict__ out1) {
+  const int e = threadIdx.x;
+  if (e >= len) return;
+  float v = 0.0f;
+  for (int p = 0; p < n_part; ++p) v += partials[(int64_t)p * stride + e];
+  if (e < split) out0[e] = v; else out1[e - split] = v;
+}
+
+inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+constexpr int kOutgradBlocks = 296;
 
 }  // namespace
 
@@ -297,65 +715,135 @@ int64_t tc_packed_bytes(const MlpLayout& L) {
   TcPlan P;
   return make_plan(L, &P) ? P.total_bytes : 0;
 }
-int64_t simt_workspace_bytes(const MlpLayout& L, int64_t n, int training);
-int64_t simt_saved_bytes(const MlpLayout& L, int64_t n);
-int simt_forward(const MlpLayout& L, const float* params, const angio_samples& in, int out_mode, float* out, void* saved,
-                 void* workspace, int64_t workspace_bytes, cudaStream_t st);
-int simt_backward(const MlpLayout& L, const float* params, const angio_samples& in, const void* saved, const float* grad_out,
-                  float* grad_params, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 
-// Training forward/backward still run the fp32 path until the tcgen05 backward lands; inference (the dominant
-// cost: the no-grad visibility pass over every marched sample) runs on tensor cores.
-int64_t tc_workspace_bytes(const MlpLayout& L, int64_t n, int training) { return training ? simt_workspace_bytes(L, n, 1) : 256; }
-int64_t tc_saved_bytes(const MlpLayout& L, int64_t n) { return simt_saved_bytes(L, n); }
+static int wgrad_groups(const MlpLayout& L) { return sm_count() / (L.n_hidden + 1) > 0 ? sm_count() / (L.n_hidden + 1) : 1; }
+
+int64_t tc_workspace_bytes(const MlpLayout& L, int64_t n, int training) {
+  if (!training) return 256;
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  const int G = wgrad_groups(L);
+  return align256((int64_t)(L.n_hidden + 1) * n_tiles * kActBytes)            // delta images
+         + align256((int64_t)(L.n_hidden + 1) * G * kWgPartial * 4)           // wgrad partials
+         + align256((int64_t)sm_count() * 32 * 4)                             // coefficient-gradient partials
+         + align256((int64_t)kOutgradBlocks * 132 * 4) + 256;                 // output-layer partials
+}
+int64_t tc_saved_bytes(const MlpLayout& L, int64_t n) {
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  return n_tiles * (kA0Bytes + (int64_t)(L.n_hidden + 1) * kActBytes) + 256;
+}
 
 int tc_pack_weights(const MlpLayout& L, const float* params, void* packed, cudaStream_t st) {
   TcPlan P;
   if (!make_plan(L, &P)) { set_error("tc_pack_weights: unsupported shape"); return ANGIO_ERR_UNSUPPORTED; }
-  const int n_w_elems = (16384 + P.n_hidden * 32768) / 2;
+  const int n_w_elems = (16384 + P.n_hidden * 32768 + 4096) / 2;
   const int total = n_w_elems > P.n_const ? n_w_elems : P.n_const;
   angio::note_launch(); pack_kernel<<<blocks_for(total, 256), 256, 0, st>>>(params, L, P, reinterpret_cast<uint8_t*>(packed));
   return finish_launch("tc_pack_weights");
 }
 
-template <int MODE>
-static int launch_fwd(const TcPlan& P, const void* packed, const angio_samples& in, float* out, cudaStream_t st) {
-  const size_t smem = (size_t)P.total_bytes + 1024;  // + slack for the 1024-byte alignment of the dynamic window
-  static size_t attr_smem = 0;  // per instantiation; one device per process
-  if (attr_smem < smem) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      cudaGetLastError();  // clear
-      set_error("cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_smem = smem;
+template <class K>
+static int ensure_smem(K kernel, size_t smem, size_t* cached) {
+  if (*cached >= smem) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("cudaFuncSetAttribute(%zu bytes): %s", smem, cudaGetErrorString(e));
+    return (int)e;
   }
+  *cached = smem;
+  return 0;
+}
+
+template <int MODE, bool TRAIN>
+static int launch_fwd(const TcPlan& P, const void* packed, const angio_samples& in, float* out, void* saved, cudaStream_t st) {
+  const size_t smem = (size_t)P.total_bytes + 1024;
+  static size_t cached = 0;
+  if (int rc = ensure_smem(mlp_fwd_tc_kernel<MODE, TRAIN>, smem, &cached)) return rc;
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
   int grid = sm_count();
   if (n_tiles < grid) grid = (int)n_tiles;
-  angio::note_launch(); mlp_fwd_tc_kernel<MODE><<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
+  angio::note_launch(); mlp_fwd_tc_kernel<MODE, TRAIN><<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out,
+                                                                                    reinterpret_cast<uint8_t*>(saved));
   return finish_launch("mlp_fwd_tc_kernel");
 }
 
 int tc_forward(const MlpLayout& L, const float* params, const void* packed, const angio_samples& in, int out_mode, float* out,
                void* saved, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
-  if (saved) return simt_forward(L, params, in, out_mode, out, saved, workspace, workspace_bytes, st);
+  (void)params; (void)workspace; (void)workspace_bytes;
   TcPlan P;
   if (!make_plan(L, &P)) { set_error("tc_forward: unsupported shape"); return ANGIO_ERR_UNSUPPORTED; }
   if (in.n == 0) return 0;
   if ((reinterpret_cast<uintptr_t>(packed) & 15) != 0) { set_error("tc_forward: packed image must be 16-byte aligned"); return ANGIO_ERR_INVALID_ARG; }
+  if (saved) {
+    if ((reinterpret_cast<uintptr_t>(saved) & 15) != 0) { set_error("tc_forward: saved buffer must be 16-byte aligned"); return ANGIO_ERR_INVALID_ARG; }
+    if (out_mode != ANGIO_OUT_LOGIT) { set_error("tc_forward: training forward returns logits only"); return ANGIO_ERR_INVALID_ARG; }
+    return launch_fwd<ANGIO_OUT_LOGIT, true>(P, packed, in, out, saved, st);
+  }
   switch (out_mode) {
-    case ANGIO_OUT_LOGIT: return launch_fwd<ANGIO_OUT_LOGIT>(P, packed, in, out, st);
-    case ANGIO_OUT_SIGMA: return launch_fwd<ANGIO_OUT_SIGMA>(P, packed, in, out, st);
-    default: return launch_fwd<ANGIO_OUT_ALPHA>(P, packed, in, out, st);
+    case ANGIO_OUT_LOGIT: return launch_fwd<ANGIO_OUT_LOGIT, false>(P, packed, in, out, nullptr, st);
+    case ANGIO_OUT_SIGMA: return launch_fwd<ANGIO_OUT_SIGMA, false>(P, packed, in, out, nullptr, st);
+    default: return launch_fwd<ANGIO_OUT_ALPHA, false>(P, packed, in, out, nullptr, st);
   }
 }
 
 int tc_backward(const MlpLayout& L, const float* params, const void* packed, const angio_samples& in, const void* saved,
                 const float* grad_out, float* grad_params, void* workspace, int64_t workspace_bytes, cudaStream_t st) {
-  (void)packed;
-  return simt_backward(L, params, in, saved, grad_out, grad_params, workspace, workspace_bytes, st);
+  (void)params;
+  TcPlan P;
+  if (!make_plan(L, &P)) { set_error("tc_backward: unsupported shape"); return ANGIO_ERR_UNSUPPORTED; }
+  cudaError_t ce = cudaMemsetAsync(grad_params, 0, L.total * 4, st);
+  if (ce != cudaSuccess) { set_error("memset grad_params: %s", cudaGetErrorString(ce)); return (int)ce; }
+  const int64_t n = in.n;
+  if (n == 0) return 0;
+  const int64_t need = tc_workspace_bytes(L, n, 1) - 256;
+  if (!workspace || workspace_bytes < need) {
+    set_error("angio_mlp_backward(bf16): workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+    return ANGIO_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 15) != 0 || (reinterpret_cast<uintptr_t>(saved) & 15) != 0) {
+    set_error("tc_backward: saved / workspace must be 16-byte aligned");
+    return ANGIO_ERR_INVALID_ARG;
+  }
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  const int G = wgrad_groups(L);
+  const int nl = L.n_hidden + 1;
+  char* wb = reinterpret_cast<char*>(workspace);
+  uint8_t* delta = reinterpret_cast<uint8_t*>(wb); wb += align256((int64_t)nl * n_tiles * kActBytes);
+  float* wpart = reinterpret_cast<float*>(wb); wb += align256((int64_t)nl * G * kWgPartial * 4);
+  float* cpart = reinterpret_cast<float*>(wb); wb += align256((int64_t)sm_count() * 32 * 4);
+  float* opart = reinterpret_cast<float*>(wb);
+  const uint8_t* sv = reinterpret_cast<const uint8_t*>(saved);
+
+  // (2) data-gradient chain
+  {
+    const size_t smem = (size_t)P.total_bytes + 1024;
+    static size_t cached = 0;
+    if (int rc = ensure_smem(mlp_dgrad_tc_kernel, smem, &cached)) return rc;
+    int grid = sm_count();
+    if (n_tiles < grid) grid = (int)n_tiles;
+    angio::note_launch(); mlp_dgrad_tc_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, sv, grad_out, delta, cpart);
+    if (int rc = finish_launch("mlp_dgrad_tc_kernel")) return rc;
+    if (L.enc) {
+      angio::note_launch(); small_reduce_kernel<<<1, 256, 0, st>>>(cpart, grid, 32, 3 * L.basis, grad_params + L.off_coef, 3 * L.basis, nullptr);
+    }
+  }
+  // (3) weight gradients
+  {
+    const size_t smem = 4096 + (size_t)kWgStages * 65536 + 1024;
+    static size_t cached = 0;
+    if (int rc = ensure_smem(mlp_wgrad_tc_kernel, smem, &cached)) return rc;
+    angio::note_launch(); mlp_wgrad_tc_kernel<<<nl * G, kWgThreads, smem, st>>>(sv, delta, n_tiles, L.n_hidden, G, wpart);
+    if (int rc = finish_launch("mlp_wgrad_tc_kernel")) return rc;
+    angio::note_launch(); wgrad_reduce_kernel<<<dim3((kWgPartial + 255) / 256, nl), 256, 0, st>>>(wpart, G, L, P, grad_params);
+  }
+  // output layer
+  {
+    const uint8_t* a_last = sv + n_tiles * kA0Bytes + (int64_t)L.n_hidden * n_tiles * kActBytes;
+    angio::note_launch(); outgrad_partial_kernel<<<kOutgradBlocks, 256, 0, st>>>(a_last, grad_out, n, n_tiles, opart);
+    const int lo = L.n_linear - 1;
+    angio::note_launch(); small_reduce_kernel<<<1, 256, 0, st>>>(opart, kOutgradBlocks, 132, 129, grad_params + L.off_w[lo], 128, grad_params + L.off_b[lo]);
+  }
+  return finish_launch("tc_backward");
 }
 
 }  // namespace angio

@@ -1,0 +1,59 @@
+"""CPU-only: the C-ABI shared library loads and exports every symbol include/angio_b200.h declares (no compute)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "angio_b200.h")).read()
+    return sorted(set(re.findall(r"ANGIO_API\s+[\w\s\*]+?\b(angio_\w+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared_symbols()
+    for must in ["angio_raygen", "angio_march_count", "angio_march_write", "angio_visibility_mask", "angio_compact_samples",
+                 "angio_mlp_forward", "angio_mlp_backward", "angio_composite_forward", "angio_composite_backward",
+                 "angio_grid_ema_update", "angio_adam_step", "angio_last_error_string", "angio_version"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    from nerf_for_angiography_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        from nerf_for_angiography_b200 import build
+        build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"{name} declared in include/angio_b200.h but not exported"
+    # the ctypes prototype table covers the header exactly
+    assert sorted(_lib.PROTOTYPES) == _declared_symbols()
+    assert _lib.load().angio_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    """error convention: negative library codes + a message, no exceptions across the ABI"""
+    from nerf_for_angiography_b200 import _lib
+    lib = _lib.load()
+    bad = _lib.MlpDesc(1, 0, 128, 4)                       # fourier with basis 0
+    assert lib.angio_mlp_param_count(ctypes.byref(bad)) == _lib.ERR_INVALID_ARG
+    assert b"invalid" in lib.angio_last_error_string()
+    good = _lib.MlpDesc(1, 5, 128, 4)
+    assert lib.angio_mlp_param_count(ctypes.byref(good)) == 70548 - 4   # reference count minus the dead img1/img2 (2+2)
+    assert lib.angio_mlp_input_width(ctypes.byref(good)) == 33
+    assert lib.angio_mlp_param_count(ctypes.byref(_lib.MlpDesc(0, 0, 128, 4))) == 66693 - 4
+    assert lib.angio_mlp_param_count(ctypes.byref(_lib.MlpDesc(1, 5, 256, 8))) == 535316 - 4
+    rc = lib.angio_raygen(None, 0, None, None, None, 10, 4, 4, 1.0, None, None, None, None, None)
+    assert rc == _lib.ERR_INVALID_ARG
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "angio_raygen")
+
+
+def test_python_surface_fails_loudly_on_cpu_tensors():
+    import torch
+    from nerf_for_angiography_b200 import ops
+    with pytest.raises(ValueError):
+        ops.composite_forward(torch.zeros(4), torch.zeros(4), torch.ones(4), torch.tensor([0, 4], dtype=torch.int32))

@@ -1,0 +1,125 @@
+"""CPU-only: analytic known-answer tests and properties of the oracle's nerfacc restatement."""
+import numpy as np
+import torch
+from hypothesis import given, settings, strategies as st
+
+from oracle import geometry as ogeo, nerfacc_ref, pipeline
+
+ROI = np.array([-100, -100, -100, 100, 100, 100], np.float32)
+
+
+def _rays(theta=0.0, phi=0.0, W=16):
+    o, d, _ = ogeo.get_ray_values(theta, phi, 0.0, [0, 0, 1500.0], W, W, 7.5 * W)
+    return o.reshape(-1, 3).astype(np.float32), d.reshape(-1, 3).astype(np.float32)
+
+
+def _grid(res, fill):
+    g = nerfacc_ref.OccupancyGrid(ROI, res)
+    g.binary[:] = fill
+    g.occs[:] = 0.5 if fill else 0.0
+    return g
+
+
+def test_central_ray_passes_through_the_origin():
+    for th, ph in [(0, 0), (45, 0), (135, 135), (354, 0)]:
+        o, d, M = ogeo.get_ray_values(th, ph, 0.0, [0, 0, 1500.0], 8, 8, 60.0)
+        c = o[4, 4] + 1500.0 * d[4, 4]          # pixel (W/2, H/2) is the principal ray
+        assert np.allclose(c, 0.0, atol=1e-9)
+        assert np.isclose(np.linalg.norm(o[0, 0]), 1500.0)
+
+
+def test_empty_grid_gives_no_samples_and_white_pixels():
+    o, d = _rays()
+    g = _grid(16, False)
+    pix, (ri, ts, te) = pipeline.render_rays(lambda x: torch.zeros(len(x), 1), g, ROI, o, d, 300, 1400.0, 1600.0, 1e-2, 1e-4)
+    assert len(ri) == 0 and torch.all(pix == 1.0)
+
+
+def test_full_grid_constant_field_matches_beer_lambert_chord():
+    o, d = _rays(W=8)
+    g = _grid(32, True)
+    logit = -4.0                                   # sigma = 0.018: transmittance stays above the early-stop threshold
+    pix, (ri, ts, te) = pipeline.render_rays(lambda x: torch.full((len(x), 1), logit), g, ROI, o, d, 300, 1400.0, 1600.0, 1e-2, 1e-4)
+    sig = 1.0 / (1.0 + np.exp(-logit))
+    tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, ROI, 1400.0, 1600.0)
+    chord = tmax - tmin
+    hit = chord > 0
+    # sum of step widths differs from the exact chord by at most one step (2/3)
+    assert np.all(np.abs(-np.log(pix.numpy()[hit]) / sig - chord[hit]) <= 2.0 / 3.0 + 1e-3)
+    counts = np.bincount(ri, minlength=len(o))
+    assert np.all(np.abs(counts[hit] - chord[hit] / (200.0 / 300.0)) <= 1.0)
+
+
+def test_single_occupied_voxel_sample_count():
+    res = 16
+    g = _grid(res, False)
+    g.binary[8, 8, 8] = True                       # voxel [0,12.5]^3
+    o = np.array([[6.0, 6.0, 1500.0]], np.float32); d = np.array([[0.0, 0.0, -1.0]], np.float32)
+    tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, ROI, 1400.0, 1600.0)
+    ri, ts, te, off = nerfacc_ref.march(o, d, tmin, tmax, ROI, res, g.binary, np.float32(200.0 / 300.0))
+    assert abs(len(ri) - 12.5 / (200.0 / 300.0)) <= 1.0       # ceil(chord / dt) +- 1
+    mid = 0.5 * (ts + te)
+    z = 1500.0 - mid
+    assert np.all((z >= -1e-3) & (z <= 12.5 + 1e-3))           # every sample midpoint lies inside the voxel
+    assert np.allclose(te - ts, 200.0 / 300.0, atol=1e-4)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.floats(0.0, 1.0))
+def test_march_structure_properties(seed, density):
+    rng = np.random.default_rng(seed)
+    res = 16
+    binary = rng.random((res,) * 3) < density
+    o, d = _rays(theta=float(rng.uniform(0, 360)), phi=float(rng.uniform(0, 180)), W=6)
+    tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, ROI, 1400.0, 1600.0)
+    ri, ts, te, off = nerfacc_ref.march(o, d, tmin, tmax, ROI, res, binary, np.float32(200.0 / 300.0))
+    assert off[0] == 0 and np.all(np.diff(off) >= 0) and off[-1] == len(ri)          # offsets monotone, sum(counts) = n
+    assert np.all(np.diff(ri) >= 0)                                                  # sorted by ray
+    for r in range(len(o)):
+        s = slice(off[r], off[r + 1])
+        assert np.all(np.diff(ts[s]) > 0) and np.all(te[s] > ts[s])                  # ascending, non-empty intervals
+        assert np.all(ts[s] >= tmin[r] - 1e-3) and np.all(0.5 * (ts[s] + te[s]) < tmax[r])
+    # every emitted midpoint sits in an occupied cell
+    mid = (0.5 * (ts + te))[:, None]
+    pts = o[ri] + mid * d[ri]
+    g = nerfacc_ref.OccupancyGrid(ROI, res); g.binary = binary
+    assert np.all(g.query_occ(pts.astype(np.float32)) == 1.0)
+
+
+@settings(max_examples=20, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1))
+def test_visibility_and_composite_properties(seed):
+    rng = np.random.default_rng(seed)
+    R = 40
+    counts = rng.integers(0, 30, R)
+    off = np.zeros(R + 1, np.int64); np.cumsum(counts, out=off[1:])
+    n = int(off[-1])
+    alphas = rng.random(n).astype(np.float32) * 0.5
+    keep = nerfacc_ref.visibility(off, alphas, 1e-2, 0.0)
+    for r in range(R):
+        k = keep[off[r]:off[r + 1]]
+        if len(k):
+            assert k[0]                                             # T_0 = 1 >= eps
+            assert np.all(np.diff(k.astype(int)) <= 0)              # once invisible, always invisible (alpha in [0,1))
+    # composite: permutation invariance within a ray and empty rays -> 1
+    ri = np.repeat(np.arange(R), counts)
+    a = np.exp(-rng.random(n)).astype(np.float32)
+    p1 = nerfacc_ref.scatter_mul(a, ri, R)
+    perm = np.concatenate([off[r] + rng.permutation(counts[r]) for r in range(R)]).astype(np.int64) if n else np.zeros(0, np.int64)
+    p2 = nerfacc_ref.scatter_mul(a[perm], ri, R)
+    assert np.allclose(p1, p2, rtol=1e-5)
+    assert np.all(p1[counts == 0] == 1.0)
+
+
+def test_grid_update_semantics():
+    g = nerfacc_ref.OccupancyGrid(ROI, 8)
+    rng = np.random.default_rng(0)
+    # step not divisible by 16: nothing happens
+    g.every_n_step(3, lambda x: np.ones(len(x), np.float32), rng=rng)
+    assert g.occs.max() == 0 and not g.binary.any()
+    # warm-up step: every cell evaluated once; threshold = min(mean, occ_thre)
+    g.every_n_step(0, lambda x: (x[:, 0] > 0).astype(np.float32) * 0.5, occ_thre=1e-2, rng=rng)
+    assert g.binary.sum() == 8 ** 3 // 2
+    before = g.occs.copy()
+    g.every_n_step(16, lambda x: np.zeros(len(x), np.float32), occ_thre=1e-2, rng=rng)
+    assert np.all(g.occs <= before) and np.all(g.occs >= before * np.float32(0.95) - 1e-9)     # EMA decay of touched cells
