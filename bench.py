@@ -186,6 +186,7 @@ def main():
     for _ in range(args.warmup):
         tr.step()
     sync_all()
+    snap = tr.snapshot()                                               # both arms are timed from this model / grid / optimiser state
     launches0 = int(lib.angio_launch_count())
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -207,10 +208,12 @@ def main():
     tr.kernel_events = None
     last_loss = float(out["loss"])
 
-    # ---------------- e2e arm: host buffers in, loss out, every step
+    # ---------------- e2e arm: host buffers in, loss out, every step (same starting state as the device-resident arm)
+    tr.restore(snap)
     for i in range(args.warmup):
         o, d, t = (x.to(dev, non_blocking=True) for x in host_batches[i])
         float(tr.step(rays=(o, d, t))["loss"])
+    tr.restore(snap)
     sync_all()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()

@@ -39,8 +39,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 8) __nanosleep(40);          // back off: leave issue slots to the warps doing the work
-    if (spins > (1u << 24)) __trap();
+    if (++spins > (1u << 26)) __trap();          // try_wait suspends in hardware until the phase flips or a time limit passes
   }
 }
 

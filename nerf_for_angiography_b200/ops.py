@@ -244,7 +244,21 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
     return s, n
 
 
-def mlp_forward(desc, params, packed, out_mode, precision, saved=False, **sample_kw):
+class BufferPool:
+    """Grow-only device scratch buffers (saved activations / workspaces) so steady-state steps never hit cudaMalloc."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes, device):
+        b = self._bufs.get(key)
+        if b is None or b.numel() < nbytes or b.device != device:
+            b = torch.empty((int(max(nbytes, 1) * 1.3) + 256,), dtype=torch.uint8, device=device)
+            self._bufs[key] = b
+        return b
+
+
+def mlp_forward(desc, params, packed, out_mode, precision, saved=False, pool=None, **sample_kw):
     """Returns out[n] (and the saved-activation buffer when saved=True)."""
     lib = _lib.load()
     params = _chk(params, torch.float32, "params", 1)
@@ -256,17 +270,17 @@ def mlp_forward(desc, params, packed, out_mode, precision, saved=False, **sample
         sb = int(lib.angio_mlp_saved_bytes(ctypes.byref(desc), n, precision))
         if sb < 0:
             raise RuntimeError("angio_mlp_saved_bytes: " + _lib.last_error())
-        saved_buf = torch.empty((max(sb, 1),), dtype=torch.uint8, device=dev)
+        saved_buf = pool.get("saved", sb, dev) if pool is not None else torch.empty((max(sb, 1),), dtype=torch.uint8, device=dev)
     wb = int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), n, precision, 0))
     if wb < 0:
         raise RuntimeError("angio_mlp_workspace_bytes: " + _lib.last_error())
-    ws = torch.empty((max(wb, 1),), dtype=torch.uint8, device=dev)
+    ws = pool.get("fwd_ws", wb, dev) if pool is not None else torch.empty((max(wb, 1),), dtype=torch.uint8, device=dev)
     _lib.check(lib.angio_mlp_forward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), int(out_mode), int(precision),
                                      _p(out), _p(saved_buf), _p(ws), wb, _stream()), "angio_mlp_forward")
     return (out, saved_buf) if saved else out
 
 
-def mlp_backward(desc, params, packed, saved_buf, grad_out, precision, grad_params=None, **sample_kw):
+def mlp_backward(desc, params, packed, saved_buf, grad_out, precision, grad_params=None, pool=None, **sample_kw):
     lib = _lib.load()
     params = _chk(params, torch.float32, "params", 1)
     grad_out = _chk(grad_out, torch.float32, "grad_out", 1)
@@ -278,7 +292,7 @@ def mlp_backward(desc, params, packed, saved_buf, grad_out, precision, grad_para
     wb = int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), n, precision, 1))
     if wb < 0:
         raise RuntimeError("angio_mlp_workspace_bytes: " + _lib.last_error())
-    ws = torch.empty((max(wb, 1),), dtype=torch.uint8, device=params.device)
+    ws = pool.get("bwd_ws", wb, params.device) if pool is not None else torch.empty((max(wb, 1),), dtype=torch.uint8, device=params.device)
     _lib.check(lib.angio_mlp_backward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), _p(saved_buf), _p(grad_out),
                                       int(precision), _p(grad_params), _p(ws), wb, _stream()), "angio_mlp_backward")
     return grad_params

@@ -37,6 +37,7 @@ class Trainer:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.packed = None
+        self.pool_bufs = ops.BufferPool()
         self.n_iter = 0
         self.lr = lr
         self.pg = process_group
@@ -105,9 +106,9 @@ class Trainer:
         if n_kept > 0:                                                      # run_nerf_acc.py:289
             prec = m._precision_id
             kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
-            logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, **kw)
+            logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
             pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world)
-            ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, **kw)
+            ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
             if self.world > 1:
                 torch.distributed.all_reduce(self.grad, group=self.pg)      # sum of per-rank (1/global-batch)-scaled grads
             ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1)
@@ -122,6 +123,21 @@ class Trainer:
         return self.last
 
     n_iter_adam = 0
+
+    # ------------------------------------------------------------------ state capture (benchmark arms start from the same state)
+    def snapshot(self):
+        grids = [g for g in (self.acc_grid, self.vessel_acc_grid) if g is not None]
+        return dict(flat=self.flat.clone(), m=self.exp_avg.clone(), v=self.exp_avg_sq.clone(), n_iter=self.n_iter,
+                    n_iter_adam=self.n_iter_adam, lr=self.lr, grids=[(g.occs.clone(), g._binary.clone(), g.occs_mean_host) for g in grids],
+                    gens=(self.ray_gen.get_state(), self.grid_gen.get_state()))
+
+    def restore(self, snap):
+        self.flat.copy_(snap["flat"]); self.exp_avg.copy_(snap["m"]); self.exp_avg_sq.copy_(snap["v"])
+        self.n_iter, self.n_iter_adam, self.lr = snap["n_iter"], snap["n_iter_adam"], snap["lr"]
+        grids = [g for g in (self.acc_grid, self.vessel_acc_grid) if g is not None]
+        for g, (occs, binary, mean) in zip(grids, snap["grids"]):
+            g.occs.copy_(occs); g._binary.copy_(binary); g.occs_mean_host = mean
+        self.ray_gen.set_state(snap["gens"][0]); self.grid_gen.set_state(snap["gens"][1])
 
     # ------------------------------------------------------------------ evaluation (run_nerf_acc.py:338-357)
     @torch.no_grad()

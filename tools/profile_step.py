@@ -56,9 +56,9 @@ def main():
         thre = min(tr.alpha_thre, g.occs_mean_host)
         ray_idx2, t02, t12, off2, _ = timed("visibility+compact", lambda: ops.visibility_compact(alphas, offsets, t0, t1, tr.early_stop_eps, thre))
         kw2 = dict(rays_o=o, rays_d=d, ray_idx=ray_idx2, t_starts=t02, t_ends=t12)
-        logits, saved = timed("mlp_forward(train)", lambda: ops.mlp_forward(m._desc, tr.flat, tr.packed, ops.OUT_LOGIT, m._precision_id, saved=True, **kw2))
+        logits, saved = timed("mlp_forward(train)", lambda: ops.mlp_forward(m._desc, tr.flat, tr.packed, ops.OUT_LOGIT, m._precision_id, saved=True, pool=tr.pool_bufs, **kw2))
         pix, gl, loss = timed("composite+mse+bwd", lambda: ops.composite_mse_fused(logits, t02, t12, off2, target, tr.n_rays))
-        timed("mlp_backward", lambda: ops.mlp_backward(m._desc, tr.flat, tr.packed, saved, gl, m._precision_id, grad_params=tr.grad, **kw2))
+        timed("mlp_backward", lambda: ops.mlp_backward(m._desc, tr.flat, tr.packed, saved, gl, m._precision_id, grad_params=tr.grad, pool=tr.pool_bufs, **kw2))
         timed("adam", lambda: ops.adam_step(tr.flat, tr.grad, tr.exp_avg, tr.exp_avg_sq, tr.lr, tr.n_iter_adam + 1))
         tr.n_iter_adam += 1
         tr.n_iter += 1

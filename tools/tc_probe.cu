@@ -7,9 +7,12 @@
 //     2  SS  A K-major,  B MN-major     (dgrad view of the same weight tile)
 //     3  SS  A MN-major, B MN-major     (wgrad view: reduction over the sample rows)
 //     4..7 throughput: 4 SS N=128, 5 TS N=128, 6 SS N=256, 7 TS N=256
+//     8  SS  bf16 inputs, D format F16 (is it legal? halves the accumulator drain)
+//     9  LDTM (tcgen05.ld) bandwidth: 4 / 8 warps reading 128 columns repeatedly
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <cuda_fp16.h>
 #include "../nerf_for_angiography_b200/csrc/tc05.cuh"
 
 using namespace tc05;
@@ -61,7 +64,8 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, con
 
   if (warp == 0 && lane == 0) {
     const uint32_t a_mn = (variant == 3), b_mn = (variant == 2 || variant == 3);
-    const uint32_t idesc = make_idesc_bf16(M, N, a_mn, b_mn);
+    uint32_t idesc = make_idesc_bf16(M, N, a_mn, b_mn);
+    if (variant == 8) idesc &= ~(3u << 4);   // D format 0 = F16
     for (int k = 0; k < K / 16; ++k) {
       // K-major: +32 B per k-step inside the 128-B row; MN-major: +16 rows * 128 B per k-step
       uint64_t da = a_mn ? make_smem_desc_sw128(smem_u32(sA) + k * 2048, 8192, 1024)
@@ -77,6 +81,18 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(const uint8_t* a_img, con
   fence_after_sync();
 
   const int row = warp * 32 + lane;
+  if (variant == 8) {
+    for (int c0 = 0; c0 < N / 2; c0 += 32) {   // packed f16x2: column c holds elements (2c, 2c+1)?
+      uint32_t r[32];
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
+      wait_ld();
+      for (int j = 0; j < 32; ++j) {
+        __half2 h = *reinterpret_cast<__half2*>(&r[j]);
+        D[row * N + 2 * (c0 + j)] = __low2float(h);
+        D[row * N + 2 * (c0 + j) + 1] = __high2float(h);
+      }
+    }
+  } else
   for (int c0 = 0; c0 < N; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, r);
@@ -126,6 +142,27 @@ __global__ void __launch_bounds__(128, 1) perf_kernel(int iters, int ts_mode, fl
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+__global__ void __launch_bounds__(256, 1) ldtm_bw_kernel(int iters, unsigned* sink) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x / 32;
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s + ((uint32_t)((warp % 4) * 32) << 16) + (warp / 4) * 128;
+  unsigned acc = 0;
+  for (int it = 0; it < iters; ++it) {
+    uint32_t r0[32], r1[32], r2[32], r3[32];
+    tmem_ld32(tmem, r0); tmem_ld32(tmem + 32, r1); tmem_ld32(tmem + 64, r2); tmem_ld32(tmem + 96, r3);
+    wait_ld();
+    for (int j = 0; j < 32; ++j) acc += r0[j] ^ r1[j] ^ r2[j] ^ r3[j];
+  }
+  if (acc == 0x12345678u) sink[threadIdx.x] = acc;
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
 static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); return (uint16_t)(u >> 16); }  // exact for small ints
 
 int main(int argc, char** argv) {
@@ -133,7 +170,25 @@ int main(int argc, char** argv) {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s sm_%d%d SMs=%d variant=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, variant);
 
-  if (variant >= 4) {
+  if (variant == 9) {
+    for (int nw = 4; nw <= 8; nw += 4) {
+      const int iters = 20000;
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      float ms = 0;
+      for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaEventRecord(e0));
+        ldtm_bw_kernel<<<prop.multiProcessorCount, nw * 32>>>(iters, nullptr);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+      }
+      double bytes_per_sm = (double)iters * nw * 32 * 128 * 4;
+      int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
+      printf("LDTM warps=%d: %.3f ms, %.1f GB/s per SM, %.1f B/clk/SM at %.0f MHz (nominal max clock)\n", nw, ms, bytes_per_sm / ms * 1e-6,
+             bytes_per_sm / (ms * 1e-3 * khz * 1e3), khz * 1e-3);
+    }
+    return 0;
+  }
+  if (variant >= 4 && variant < 8) {
     const int NN = (variant >= 6) ? 256 : 128, ts = (variant & 1);
     const int iters = 4096;
     size_t smem = 32768 + NN * 256 + 1024;
