@@ -58,6 +58,16 @@ ANGIO_API int angio_raygen(const double* cam2world, int32_t view0, const int32_t
                  const float* pixels, float* rays_o, float* rays_d, float* pix_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Weighted ray sampling without replacement.   Replaces DataFrame.sample(n, weights) in sample_pixel_rays
+ * (nerf/nerf_helpers.py:137-150).  Exponential race: key_i = -log(u_i)/w_i, u from a counter-based hash of
+ * (seed, i); rays with key < tau are appended to (cand_keys, cand_ids) (capacity entries; *counter must be 0 on
+ * entry and receives the number of candidates).  The caller takes the n smallest keys.  weights may be NULL
+ * (uniform).  cand_keys should be pre-filled with +inf so unfilled slots never win.
+ */
+ANGIO_API int angio_sample_candidates(const float* weights, int64_t n_pool, uint64_t seed, float tau, int32_t capacity,
+                                      float* cand_keys, int64_t* cand_ids, int32_t* counter, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Occupancy-grid ray marching.   Replaces nerfacc.ray_marching's slab test + two-pass
  * _C.ray_marching (called at nerf/nerf_helpers_acc.py:29).  binary: [res,res,res] uint8 (torch.bool),
  * x-major.  roi / aabb: 6 floats (min xyz, max xyz) on the HOST.

@@ -15,5 +15,6 @@ from .nerf.nerf_helpers_acc import acc_ray_marching, acc_render_volume_density, 
 from .nerf.nerf_helpers import get_predictions, sample_pixel_rays  # noqa: F401
 from .render import render_rays  # noqa: F401
 from .geometry import get_ray_values, source_matrix  # noqa: F401
+from .inference import query_volume, render_projections  # noqa: F401
 
 __version__ = "0.1.0"

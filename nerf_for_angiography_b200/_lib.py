@@ -31,6 +31,7 @@ PROTOTYPES = {
     "angio_last_error_string": (ctypes.c_char_p, []),
     "angio_sm_count": (c_i32, []),
     "angio_launch_count": (c_i64, []),
+    "angio_sample_candidates": (c_i32, [c_ptr, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_raygen": (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_march_count": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_exclusive_scan_i32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),

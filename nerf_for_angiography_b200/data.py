@@ -116,6 +116,7 @@ class RayPool:
         self.weights = None if weights is None else weights.contiguous().float()
         self.n_rays = self.n_views * self.img_h * self.img_w
         self._wsum = None
+        self._seed_streams = {}
 
     @property
     def device(self):
@@ -135,26 +136,27 @@ class RayPool:
         if n > N:
             raise ValueError("cannot sample more rays than the pool holds without replacement")
         w = self.weights if weights is None else weights
-        u = torch.rand(N, device=dev, generator=generator).clamp_min_(1e-30)
-        keys = -torch.log(u)
         if w is not None:
-            wf = w.reshape(-1)
-            keys = keys / wf
-            if self._wsum is None or weights is not None:
+            wf = w.reshape(-1).contiguous().float()
+            if weights is not None:
                 wsum = float(wf.sum().item())
-                if weights is None:
-                    self._wsum = wsum
             else:
+                if self._wsum is None:
+                    self._wsum = float(wf.sum().item())
                 wsum = self._wsum
         else:
-            wsum = float(N)
-        target = n + 6.0 * math.sqrt(n) + 16.0
-        tau = target / wsum
-        cand = torch.nonzero(keys < tau)[:, 0] if target < 0.5 * N else None
-        if cand is None or cand.numel() < n:
-            cand = torch.arange(N, device=dev)
-        sel = cand[torch.topk(keys[cand], n, largest=False).indices]
-        return sel[torch.randperm(n, device=dev, generator=generator)]
+            wf, wsum = None, float(N)
+        # per-call 62-bit seed from a host-side stream tied to the torch generator's seed: reproducible, rank-dependent,
+        # and no device->host sync
+        key = id(generator) if generator is not None else None
+        rng = self._seed_streams.get(key)
+        if rng is None:
+            rng = np.random.default_rng(generator.initial_seed() if generator is not None else None)
+            self._seed_streams[key] = rng
+        seed = int(rng.integers(0, 2 ** 62))
+        sel, _ = ops.sample_without_replacement(n, N, wf, wsum, seed, dev)
+        cuda_gen = generator if (generator is not None and generator.device.type == "cuda") else None
+        return sel[torch.randperm(n, device=dev, generator=cuda_gen)]
 
     def gather(self, ids):
         hw = self.img_h * self.img_w

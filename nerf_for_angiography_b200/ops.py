@@ -69,6 +69,25 @@ def raygen(cam2world, img_w, img_h, focal, view=0, view_ids=None, px=None, py=No
     return (o, d, pix) if pix is not None else (o, d)
 
 
+def sample_without_replacement(n, n_pool, weights, wsum, seed, device):
+    """n ids out of n_pool, weighted, without replacement (exponential race + threshold pre-filter).  No host sync."""
+    lib = _lib.load()
+    import math
+    weights = _chk(weights, torch.float32, "weights", 1, allow_none=True)
+    target = n + 8.0 * math.sqrt(n) + 32.0
+    if target >= 0.5 * n_pool:                      # tiny pools: every ray is a candidate
+        tau, capacity = 3.0e38, int(n_pool)
+    else:
+        tau, capacity = target / float(wsum), int(n + 16.0 * math.sqrt(n) + 64)
+    keys = torch.full((capacity,), float("inf"), dtype=torch.float32, device=device)
+    ids = torch.zeros((capacity,), dtype=torch.int64, device=device)
+    counter = torch.zeros((1,), dtype=torch.int32, device=device)
+    _lib.check(lib.angio_sample_candidates(_p(weights), int(n_pool), int(seed) & 0xFFFFFFFFFFFFFFFF, float(tau), capacity, _p(keys),
+                                           _p(ids), _p(counter), _stream()), "angio_sample_candidates")
+    sel = torch.topk(keys, n, largest=False, sorted=False).indices
+    return ids[sel], counter
+
+
 # ------------------------------------------------------------------------------------------------ marching
 def exclusive_scan(counts):
     lib = _lib.load()

@@ -293,3 +293,33 @@ def test_adam_matches_torch(A):
         ref.grad = g.clone(); opt.step()
         A.ops.adam_step(gp, g.cuda(), m, v, 1e-4, step)
         assert torch.allclose(gp.cpu(), ref.detach(), rtol=1e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------------ ray sampling
+def test_weighted_sampling_without_replacement(A):
+    from nerf_for_angiography_b200.data import RayPool
+    V, H, W = 3, 40, 50
+    torch.manual_seed(0)
+    w = torch.rand(V, H, W, device="cuda") ** 2 + 1e-3
+    w[1] *= 5.0                                             # view 1 five times as likely
+    pool = RayPool(torch.eye(4, dtype=torch.float64, device="cuda").repeat(V, 1, 1), torch.rand(V, H, W, device="cuda"), 100.0, w)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 1500
+    counts = torch.zeros(V * H * W, device="cuda")
+    for _ in range(60):
+        ids = pool.sample_ids(n, generator=g)
+        assert ids.numel() == n and ids.unique().numel() == n      # without replacement
+        assert int(ids.min()) >= 0 and int(ids.max()) < V * H * W
+        counts[ids] += 1
+    # inclusion frequency follows the weights (n << N: probability ~ n * w / sum w)
+    expect = (n * w.reshape(-1) / w.sum()).clamp(max=1.0) * 60
+    view_got = counts.view(V, -1).sum(1)
+    view_exp = expect.view(V, -1).sum(1)
+    assert torch.allclose(view_got, view_exp, rtol=0.06), (view_got, view_exp)
+    # all rays requested -> a permutation of the pool
+    ids = pool.sample_ids(V * H * W, generator=g)
+    assert ids.sort().values.equal(torch.arange(V * H * W, device="cuda"))
+    # uniform pool
+    pool_u = RayPool(pool.cam2world, pool.pixels, 100.0, None)
+    ids = pool_u.sample_ids(1000, generator=g)
+    assert ids.unique().numel() == 1000

@@ -300,3 +300,35 @@ def _decode_saved_images(saved_u8, n, L, basis):
         buf[:n * 128 * 4] = np.ascontiguousarray(act).reshape(-1).view(np.uint8)
         parts.append(buf)
     return torch.from_numpy(np.concatenate(parts)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------ inference entry points
+def test_inference_render_projections_and_volume_query(A):
+    og, gg, roi, _, _ = _small_scene(A)
+    p = _scaled_params(2, 64, "fourier", 9)
+    model = A.CPPN(_model_def(2, 64, "fourier", "fp32"))
+    model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda")
+    f = functools.partial(ocppn.cppn_forward, p, pos_enc="fourier", basis=5)
+    W, H, focal = 14, 10, 105.0                                        # W != H: catches x/y transposition
+    views = [(30.0, 0.0), (135.0, 135.0)]
+    imgs, bins = A.render_projections(model, gg, torch.tensor(roi).cuda(), views, np.array([0, 0, 1500.0]), W, H, focal, 300, 1400.0,
+                                      1600.0, 1e-2, 1e-4, binary_thresh=0.05)
+    assert imgs.shape == (2, H, W)
+    for v, (th, ph) in enumerate(views):
+        o, d, _ = ogeo.get_ray_values(th, ph, 0.0, [0, 0, 1500.0], W, H, focal)
+        with torch.no_grad():
+            ref, (ri, ts, te) = pipeline.render_rays(f, og, roi, o.reshape(-1, 3).astype(np.float32), d.reshape(-1, 3).astype(np.float32),
+                                                     300, 1400.0, 1600.0, 1e-2, 1e-4)
+        assert np.max(np.abs(imgs[v].cpu().numpy().reshape(-1) - ref.numpy())) <= 1e-5
+        assert float(bins[v].min()) >= float(imgs[v].min()) - 1e-6     # zeroing sigma can only brighten the projection
+    # volume query on the reference's 'xy' meshgrid lattice
+    t = np.linspace(-75, 75, 7).astype(np.float32)
+    vol = A.query_volume(model, t).cpu().numpy()
+    mesh = np.stack(np.meshgrid(t, t, t), -1).reshape(-1, 3)           # visualization.py:209-211
+    with torch.no_grad():
+        ref = torch.sigmoid(f(torch.from_numpy(mesh))).reshape(7, 7, 7).numpy()
+    assert np.max(np.abs(vol - ref)) <= 1e-5
+    masked = A.query_volume(model, t, grid=gg).cpu().numpy()
+    occ = og.query_occ(mesh).reshape(7, 7, 7)
+    assert np.max(np.abs(masked - ref * occ)) <= 1e-5
