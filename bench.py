@@ -193,6 +193,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tr.kernel_events, tr.kernel_samples = [], []                       # event pairs around the visibility-pass MLP launch
     n_pre_total = n_kept_total = 0
+    torch.cuda.profiler.start()                                        # ncu --profile-from-start off captures exactly the timed region
     e0.record()
     for _ in range(args.steps):
         out = tr.step()
@@ -200,6 +201,7 @@ def main():
         n_kept_total += out["n_samples"]
     e1.record()
     sync_all()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     launches = int(lib.angio_launch_count()) - launches0

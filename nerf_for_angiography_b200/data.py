@@ -139,13 +139,13 @@ class RayPool:
         if w is not None:
             wf = w.reshape(-1).contiguous().float()
             if weights is not None:
-                wsum = float(wf.sum().item())
+                wsum, wsum2 = float(wf.sum().item()), float((wf.double() ** 2).sum().item())
             else:
                 if self._wsum is None:
-                    self._wsum = float(wf.sum().item())
-                wsum = self._wsum
+                    self._wsum = (float(wf.sum().item()), float((wf.double() ** 2).sum().item()))
+                wsum, wsum2 = self._wsum
         else:
-            wf, wsum = None, float(N)
+            wf, wsum, wsum2 = None, float(N), float(N)
         # per-call 62-bit seed from a host-side stream tied to the torch generator's seed: reproducible, rank-dependent,
         # and no device->host sync
         key = id(generator) if generator is not None else None
@@ -154,7 +154,7 @@ class RayPool:
             rng = np.random.default_rng(generator.initial_seed() if generator is not None else None)
             self._seed_streams[key] = rng
         seed = int(rng.integers(0, 2 ** 62))
-        sel, _ = ops.sample_without_replacement(n, N, wf, wsum, seed, dev)
+        sel, _ = ops.sample_without_replacement(n, N, wf, wsum, wsum2, seed, dev)
         cuda_gen = generator if (generator is not None and generator.device.type == "cuda") else None
         return sel[torch.randperm(n, device=dev, generator=cuda_gen)]
 

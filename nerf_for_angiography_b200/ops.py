@@ -69,23 +69,29 @@ def raygen(cam2world, img_w, img_h, focal, view=0, view_ids=None, px=None, py=No
     return (o, d, pix) if pix is not None else (o, d)
 
 
-def sample_without_replacement(n, n_pool, weights, wsum, seed, device):
-    """n ids out of n_pool, weighted, without replacement (exponential race + threshold pre-filter).  No host sync."""
-    lib = _lib.load()
+def sample_without_replacement(n, n_pool, weights, wsum, wsum2, seed, device):
+    """n ids out of n_pool, weighted, without replacement (exponential race + threshold pre-filter).  No host sync.
+
+    The expected number of rays with key < tau is sum_i (1 - exp(-w_i tau)), bracketed by tau*S1 - tau^2*S2/2 and tau*S1
+    (S1 = sum w, S2 = sum w^2): tau is chosen from the lower bound so at least n + 8 sigma candidates are expected, the
+    candidate buffers are sized from the upper bound.  Small pools / large sampling fractions consider every ray."""
     import math
+    lib = _lib.load()
     weights = _chk(weights, torch.float32, "weights", 1, allow_none=True)
     target = n + 8.0 * math.sqrt(n) + 32.0
-    if target >= 0.5 * n_pool:                      # tiny pools: every ray is a candidate
+    disc = wsum * wsum - 2.0 * wsum2 * target
+    if n > 0.1 * n_pool or disc <= 0.0:
         tau, capacity = 3.0e38, int(n_pool)
     else:
-        tau, capacity = target / float(wsum), int(n + 16.0 * math.sqrt(n) + 64)
+        tau = (wsum - math.sqrt(disc)) / wsum2
+        capacity = min(int(n_pool), int(tau * wsum + 10.0 * math.sqrt(tau * wsum) + 64))
     keys = torch.full((capacity,), float("inf"), dtype=torch.float32, device=device)
-    ids = torch.zeros((capacity,), dtype=torch.int64, device=device)
+    ids = torch.full((capacity,), -1, dtype=torch.int64, device=device)
     counter = torch.zeros((1,), dtype=torch.int32, device=device)
     _lib.check(lib.angio_sample_candidates(_p(weights), int(n_pool), int(seed) & 0xFFFFFFFFFFFFFFFF, float(tau), capacity, _p(keys),
                                            _p(ids), _p(counter), _stream()), "angio_sample_candidates")
-    sel = torch.topk(keys, n, largest=False, sorted=False).indices
-    return ids[sel], counter
+    order = torch.sort(keys).indices[:n]                 # the n smallest keys (unfilled slots hold +inf)
+    return ids[order], counter
 
 
 # ------------------------------------------------------------------------------------------------ marching

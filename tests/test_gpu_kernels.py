@@ -311,11 +311,16 @@ def test_weighted_sampling_without_replacement(A):
         assert ids.numel() == n and ids.unique().numel() == n      # without replacement
         assert int(ids.min()) >= 0 and int(ids.max()) < V * H * W
         counts[ids] += 1
-    # inclusion frequency follows the weights (n << N: probability ~ n * w / sum w)
-    expect = (n * w.reshape(-1) / w.sum()).clamp(max=1.0) * 60
-    view_got = counts.view(V, -1).sum(1)
-    view_exp = expect.view(V, -1).sum(1)
-    assert torch.allclose(view_got, view_exp, rtol=0.06), (view_got, view_exp)
+    # inclusion frequencies match numpy's sequential weighted sampling without replacement -- what pandas'
+    # DataFrame.sample(n, weights=...) does (nerf/nerf_helpers.py:139) -- here at a 25 % sampling fraction where heavy rays saturate
+    wn = w.reshape(-1).double().cpu().numpy(); wn /= wn.sum()
+    rng = np.random.default_rng(0)
+    ref = np.zeros(V * H * W)
+    for _ in range(60):
+        ref[rng.choice(V * H * W, n, replace=False, p=wn)] += 1
+    view_got = counts.view(V, -1).sum(1).cpu().numpy()
+    view_ref = ref.reshape(V, -1).sum(1)
+    assert np.allclose(view_got, view_ref, rtol=0.03), (view_got, view_ref)
     # all rays requested -> a permutation of the pool
     ids = pool.sample_ids(V * H * W, generator=g)
     assert ids.sort().values.equal(torch.arange(V * H * W, device="cuda"))
