@@ -43,14 +43,28 @@ def model_def(w, device, precision):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py) from a background thread --
+    the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, without forking a process that
+    polls the driver while the step is being timed.  Falls back to the nvidia-smi loop if NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, period_s=0.02):
+        self.rows, self.proc, self.index, self.period = [], None, index, period_s
+        self.nvml, self.handle, self.thread, self.stop_flag, self.sm_max = None, None, None, False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -58,11 +72,31 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((sm, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted({k for r in self.rows for k in r[1]})
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
+                    "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -72,7 +106,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def cpu_oracle_step_time(w, n_rays_cpu, steps=1, seed=0):
@@ -142,6 +176,7 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -189,7 +224,8 @@ def main():
     snap = tr.snapshot()                                               # both arms are timed from this model / grid / optimiser state
     launches0 = int(lib.angio_launch_count())
     clocks = ClockSampler(local_rank)
-    clocks.start()
+    if not args.no_clocks:
+        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tr.kernel_events, tr.kernel_samples = [], []                       # event pairs around the visibility-pass MLP launch
     n_pre_total = n_kept_total = 0
@@ -203,7 +239,7 @@ def main():
     sync_all()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
+    clk = clocks.stop() if not args.no_clocks else None
     launches = int(lib.angio_launch_count()) - launches0
     kernel_ms = [a.elapsed_time(b) for a, b in tr.kernel_events]
     kernel_n = list(tr.kernel_samples)

@@ -67,6 +67,19 @@ ANGIO_API int angio_raygen(const double* cam2world, int32_t view0, const int32_t
 ANGIO_API int angio_sample_candidates(const float* weights, int64_t n_pool, uint64_t seed, float tau, int32_t capacity,
                                       float* cand_keys, int64_t* cand_ids, int32_t* counter, void* stream);
 
+/* One-call sampler: candidates (above) -> exact selection of the n smallest keys (radix select) -> uniform shuffle
+ * (the `.sample(frac=1)` of nerf/nerf_helpers.py:139), all stream-ordered, no host sync.  ids_out: [n] int64 flat ray ids
+ * (view * H * W + y * W + x).  status: 2 x int32 on the device: [0] = number of candidates, [1] = 1 if the candidate
+ * buffer overflowed or held fewer than n rays (ids_out is then undefined; re-draw with a larger tau / capacity).
+ * The permutation depends only on (seed, selected set): reproducible although candidates are appended in arbitrary order.
+ */
+ANGIO_API int64_t angio_sample_rays_workspace_bytes(int32_t capacity, int64_t n);
+ANGIO_API int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n, uint64_t seed, float tau, int32_t capacity,
+                                int64_t* ids_out, int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
+/* angio_raygen in gather mode driven by flat ray ids (the sampler's output); pixels: [n_views, H, W] -> pix_out[n] */
+ANGIO_API int angio_raygen_flat(const double* cam2world, const int64_t* ids, int64_t n, int32_t img_w, int32_t img_h,
+                                double focal, const float* pixels, float* rays_o, float* rays_d, float* pix_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Occupancy-grid ray marching.   Replaces nerfacc.ray_marching's slab test + two-pass
  * _C.ray_marching (called at nerf/nerf_helpers_acc.py:29).  binary: [res,res,res] uint8 (torch.bool),
@@ -128,6 +141,9 @@ typedef struct angio_samples {
   const int32_t* ray_idx; /* [n] */
   const float* t_starts;  /* [n] */
   const float* t_ends;    /* [n] */
+  const int32_t* n_dev;   /* optional DEVICE-resident sample count: kernels process min(*n_dev, n) samples, so a marcher
+                             that leaves its total on the device can feed the MLP without a host sync (n = capacity of
+                             the arrays).  Supported by the bf16 inference forward; NULL everywhere else. */
 } angio_samples;
 
 #define ANGIO_OUT_LOGIT 0 /* raw model output (CPPN.forward)                                   */

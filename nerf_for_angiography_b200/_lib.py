@@ -19,7 +19,7 @@ class MlpDesc(ctypes.Structure):
 class Samples(ctypes.Structure):
     """angio_samples"""
     _fields_ = [("n", c_i64), ("points", c_ptr), ("rays_o", c_ptr), ("rays_d", c_ptr), ("ray_idx", c_ptr),
-                ("t_starts", c_ptr), ("t_ends", c_ptr)]
+                ("t_starts", c_ptr), ("t_ends", c_ptr), ("n_dev", c_ptr)]
 
 
 _P_DESC = ctypes.POINTER(MlpDesc)
@@ -32,6 +32,9 @@ PROTOTYPES = {
     "angio_sm_count": (c_i32, []),
     "angio_launch_count": (c_i64, []),
     "angio_sample_candidates": (c_i32, [c_ptr, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_sample_rays_workspace_bytes": (c_i64, [c_i32, c_i64]),
+    "angio_sample_rays": (c_i32, [c_ptr, c_i64, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "angio_raygen_flat": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_raygen": (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_march_count": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_exclusive_scan_i32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),

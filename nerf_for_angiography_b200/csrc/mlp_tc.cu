@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
   __shared__ PipeBarriers bars;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
-  const int64_t n = in.n;
+  int64_t n = in.n;
+  if (in.n_dev) { const int64_t nd = *in.n_dev; n = nd < n ? nd : n; }   // device-resident count (sync-free marcher -> MLP)
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...; slot = j & 1
   const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;

@@ -1,10 +1,16 @@
-// sampler.cu -- weighted ray sampling WITHOUT replacement over the whole ray pool.
-// Replaces sample_pixel_rays' `DataFrame.sample(n, weights)` (/root/reference/nerf/nerf_helpers.py:137-150; 27.5 ms of
-// serial pandas work per iteration at reference scale).  Exponential-race formulation of sampling without replacement
-// (Efraimidis-Spirakis): key_i = -log(u_i) / w_i, the n smallest keys are the sample.  One pass over the pool computes
-// the keys from a counter-based hash RNG and keeps only candidates below a threshold tau chosen so that ~n + 8 sigma
-// survive; survivors are appended with warp-aggregated atomics.  The caller finishes with a top-n over the few
-// survivors.  HBM-bound: 4 B/ray when weights are given, nothing at all for uniform weights.
+// sampler.cu -- weighted ray sampling WITHOUT replacement over the whole ray pool, then a uniform shuffle.
+// Replaces sample_pixel_rays' `DataFrame.sample(n, weights).sample(frac=1)` (/root/reference/nerf/nerf_helpers.py:137-150;
+// 27.5 ms of serial pandas work per iteration at reference scale).
+//
+// Exponential-race formulation of sampling without replacement (Efraimidis-Spirakis): key_i = E_i / w_i with
+// E_i ~ Exp(1); the n smallest keys are the sample.
+//   pass 1 (all SMs)   one sweep over the pool: keys from a counter-based hash RNG, only candidates below a threshold tau
+//                      (chosen by the caller so that ~n + 8 sigma survive) are appended with warp-aggregated atomics.
+//                      HBM-bound: 4 B/ray when weights are given, nothing at all for uniform weights.
+//   pass 2 (4 small kernels over the ~n candidates, L2 resident) exact radix select of the n-th smallest key, then the
+//                      survivors are ordered by an independent hash of their ray id (bucket sort) -- a uniformly random
+//                      permutation that is a pure function of (seed, selected set), i.e. reproducible run to run although
+//                      pass 1 appends in arbitrary order.
 #include "common.cuh"
 
 namespace {
@@ -13,6 +19,16 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {   // splitmix64 finalise
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
+}
+
+// E ~ Exp(1) from 48 hash bits.  E = -log(1 - v), v uniform in (0, 1) built so that SMALL v (the keys that can win the
+// race) keep 24 significant bits: a 24-bit grid alone would give only ~n distinct winning keys.
+__device__ __forceinline__ float exp_variate(uint64_t h) {
+  const float hi = (float)(uint32_t)(h >> 40);             // 24 bits
+  const float lo = (float)(uint32_t)((h >> 16) & 0xFFFFFFu);
+  const float v = (hi + (lo + 0.5f) * (1.0f / 16777216.0f)) * (1.0f / 16777216.0f);
+  if (v < 0.015625f) return v * (1.0f + v * (0.5f + v * (1.0f / 3.0f)));   // series of -log(1-v), rel. error < v^3/4
+  return -__logf(fmaxf(1.0f - v, 1e-30f));
 }
 
 __global__ void __launch_bounds__(256) sample_candidates_kernel(const float* __restrict__ weights, int64_t n_pool, uint64_t seed,
@@ -25,9 +41,8 @@ __global__ void __launch_bounds__(256) sample_candidates_kernel(const float* __r
     float key = 0.0f;
     if (i < n_pool) {
       const uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(i + 1));
-      const float u = ((float)(uint32_t)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
       const float w = weights ? weights[i] : 1.0f;
-      key = -__logf(u) / w;
+      key = exp_variate(h) / w;
       take = (w > 0.0f) && (key < tau);
     }
     const unsigned m = __ballot_sync(0xffffffffu, take);
@@ -43,6 +58,209 @@ __global__ void __launch_bounds__(256) sample_candidates_kernel(const float* __r
   }
 }
 
+// ---- pass 2: exact selection + shuffle over the m ~ n + 8 sqrt(n) candidates (L2 resident)
+//   select_kernel   (1 CTA)    radix select of the n-th smallest key -> ctl[1] = its bit pattern, ctl[2] = ties to take
+//   mark_kernel     (many CTAs) flag the sample (the flag is the ray's shuffle hash, it replaces the key) + bucket histogram
+//   scatter_kernel  (many CTAs) every CTA scans the <= 4096 bucket counts itself, then scatters (hash, id) into its bucket
+//   bucket_sort_kernel (warp per bucket) orders each ~32-ray bucket by (hash, id) and writes the final ids
+constexpr int kSelThreads = 1024;
+constexpr int kMaxBuckets = 4096;
+
+__device__ __forceinline__ uint32_t shuffle_hash(int64_t id, uint64_t seed) {
+  return (uint32_t)(mix64((seed ^ 0xD1B54A32D192ED03ull) + 0x9E3779B97F4A7C15ull * (uint64_t)(id + 1)) >> 32);
+}
+
+// ctl: [0] candidate counter, [1] threshold key bits, [2] ties to take, [3] ties taken
+__global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const float* __restrict__ cand_keys, int32_t* __restrict__ ctl, int32_t capacity,
+                                                                int32_t n, int32_t* __restrict__ status) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_need;
+  const int tid = threadIdx.x;
+  const int count = ctl[0];
+  const int m = min(count, capacity);
+  const uint32_t* kb = reinterpret_cast<const uint32_t*>(cand_keys);   // keys are positive floats: their bit patterns order like the values
+  if (tid == 0) {
+    s_prefix = 0; s_need = (uint32_t)n;
+    status[0] = count;
+    status[1] = (count > capacity || m < n) ? 1 : 0;        // overflow / too few candidates: the caller re-draws with a larger tau
+  }
+  __syncthreads();
+  if (m < n) return;
+  uint32_t mask = 0;
+  for (int pass = 0; pass < 4; ++pass) {                     // MSB first, 8 bits per pass
+    const int shift = 24 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int i0 = 0; i0 < m; i0 += kSelThreads) {
+      const int i = i0 + tid;
+      const uint32_t b = (i < m) ? kb[i] : 0u;
+      const bool hit = (i < m) && ((b & mask) == prefix);
+      // warp-aggregated histogram: the winning keys share their leading bits, so a plain atomicAdd serialises on one bin
+      const uint32_t digit = hit ? (b >> shift) & 255u : 256u;
+      const unsigned peers = __match_any_sync(0xffffffffu, digit);
+      if (hit && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {                                          // warp 0 finds the digit that holds the s_need-th key
+      const uint32_t need = s_need;
+      uint32_t loc[8], sum = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { loc[k] = hist[tid * 8 + k]; sum += loc[k]; }
+      uint32_t inc = sum;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+      uint32_t cum = inc - sum;                              // keys in the digits before this lane's 8
+      if (cum < need && need <= inc) {
+        int d = 0;
+        for (; d < 8; ++d) { if (cum + loc[d] >= need) break; cum += loc[d]; }
+        s_need = need - cum;
+        s_prefix = prefix | ((uint32_t)(tid * 8 + d) << shift);
+      }
+    }
+    mask |= 255u << shift;
+    __syncthreads();
+  }
+  if (tid == 0) { ctl[1] = (int32_t)s_prefix; ctl[2] = (int32_t)s_need; ctl[3] = 0; }
+}
+
+__device__ __forceinline__ uint32_t bucket_of(uint32_t flag, int log2_buckets) { return log2_buckets ? flag >> (32 - log2_buckets) : 0u; }
+
+__global__ void __launch_bounds__(256) mark_kernel(float* __restrict__ cand_keys, const int64_t* __restrict__ cand_ids, int32_t* __restrict__ ctl,
+                                                   int32_t capacity, int32_t n, uint64_t seed, int32_t log2_buckets,
+                                                   uint32_t* __restrict__ bcount) {
+  const int m = min(ctl[0], capacity);
+  if (m < n) return;
+  const uint32_t T = (uint32_t)ctl[1], need_ties = (uint32_t)ctl[2];
+  uint32_t* kb = reinterpret_cast<uint32_t*>(cand_keys);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t b = kb[i];
+    bool sel = b < T;
+    if (b == T) sel = (uint32_t)atomicAdd(&ctl[3], 1) < need_ties;   // exact ties at the threshold: any of them (measure zero)
+    uint32_t flag = 0xFFFFFFFFu;
+    if (sel) {
+      flag = shuffle_hash(cand_ids[i], seed);
+      if (flag == 0xFFFFFFFFu) flag = 0xFFFFFFFEu;
+      atomicAdd(&bcount[bucket_of(flag, log2_buckets)], 1u);
+    }
+    kb[i] = flag;
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads) scatter_kernel(const float* __restrict__ cand_keys, const int64_t* __restrict__ cand_ids,
+                                                             const int32_t* __restrict__ ctl, int32_t capacity, int32_t n, int32_t n_buckets,
+                                                             int32_t log2_buckets, const uint32_t* __restrict__ bcount, uint32_t* __restrict__ bfill,
+                                                             uint32_t* __restrict__ bstart_out, uint32_t* __restrict__ tmp_hash,
+                                                             int64_t* __restrict__ tmp_ids) {
+  __shared__ uint32_t bstart[kMaxBuckets + 1];
+  __shared__ uint32_t scan_tmp[kSelThreads / 32];
+  const int tid = threadIdx.x;
+  const int m = min(ctl[0], capacity);
+  if (m < n) return;
+  {   // exclusive scan of the bucket counts (n_buckets <= 4096 = 4 per thread), redone by every CTA
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int b = tid * 4 + k; v[k] = (b < n_buckets) ? bcount[b] : 0u; sum += v[k]; }
+    uint32_t inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) scan_tmp[tid / 32] = inc;
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t w = scan_tmp[tid], winc = w;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (tid >= o) winc += t; }
+      scan_tmp[tid] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = scan_tmp[tid / 32] + inc - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int b = tid * 4 + k; if (b < n_buckets) { bstart[b] = run; run += v[k]; } }
+    if (tid == kSelThreads - 1) bstart[n_buckets] = run;
+    __syncthreads();
+    if (blockIdx.x == 0)
+      for (int b = tid; b <= n_buckets; b += kSelThreads) bstart_out[b] = bstart[b];
+  }
+  const uint32_t* kb = reinterpret_cast<const uint32_t*>(cand_keys);
+  for (int i = blockIdx.x * blockDim.x + tid; i < m; i += gridDim.x * blockDim.x) {
+    const uint32_t flag = kb[i];
+    if (flag != 0xFFFFFFFFu) {
+      const uint32_t b = bucket_of(flag, log2_buckets);
+      const uint32_t pos = bstart[b] + atomicAdd(&bfill[b], 1u);        // arbitrary order inside a bucket; the sort fixes it
+      tmp_hash[pos] = flag;
+      tmp_ids[pos] = cand_ids[i];
+    }
+  }
+}
+
+// Buckets hold ~32 rays: the common case (<= 64) keeps them in registers and compares through shuffles.
+__global__ void __launch_bounds__(256) bucket_sort_kernel(const int32_t* __restrict__ ctl, int32_t capacity, int32_t n, int32_t n_buckets,
+                                                          const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ tmp_hash,
+                                                          const int64_t* __restrict__ tmp_ids, int64_t* __restrict__ ids_out) {
+  if (min(ctl[0], capacity) < n) return;
+  const int lane = threadIdx.x % 32;
+  const int b = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (b >= n_buckets) return;
+  const uint32_t s0 = bstart[b], cnt = bstart[b + 1] - s0;
+  if (cnt == 0) return;
+  if (cnt <= 64) {
+    const bool v0 = (uint32_t)lane < cnt, v1 = (uint32_t)lane + 32 < cnt;
+    const uint32_t h0 = v0 ? tmp_hash[s0 + lane] : 0u, h1 = v1 ? tmp_hash[s0 + lane + 32] : 0u;
+    const int64_t i0 = v0 ? tmp_ids[s0 + lane] : 0, i1 = v1 ? tmp_ids[s0 + lane + 32] : 0;
+    uint32_t r0 = 0, r1 = 0;
+    const int c0 = cnt < 32 ? (int)cnt : 32;
+    for (int j = 0; j < c0; ++j) {
+      const uint32_t hj = __shfl_sync(0xffffffffu, h0, j);
+      const int64_t ij = __shfl_sync(0xffffffffu, i0, j);
+      r0 += (hj < h0) || (hj == h0 && ij < i0);
+      r1 += (hj < h1) || (hj == h1 && ij < i1);
+    }
+    for (int j = 32; j < (int)cnt; ++j) {
+      const uint32_t hj = __shfl_sync(0xffffffffu, h1, j - 32);
+      const int64_t ij = __shfl_sync(0xffffffffu, i1, j - 32);
+      r0 += (hj < h0) || (hj == h0 && ij < i0);
+      r1 += (hj < h1) || (hj == h1 && ij < i1);
+    }
+    if (v0) ids_out[s0 + r0] = i0;
+    if (v1) ids_out[s0 + r1] = i1;
+  } else {
+    for (uint32_t e = lane; e < cnt; e += 32) {
+      const uint32_t he = tmp_hash[s0 + e];
+      const int64_t ie = tmp_ids[s0 + e];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < cnt; ++j) {
+        const uint32_t hj = tmp_hash[s0 + j];
+        rank += (hj < he) || (hj == he && tmp_ids[s0 + j] < ie);
+      }
+      ids_out[s0 + rank] = ie;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) raygen_flat_kernel(const double* __restrict__ cam2world, const int64_t* __restrict__ ids, int64_t n,
+                                                          int img_w, int img_h, double focal, const float* __restrict__ pixels,
+                                                          float* __restrict__ rays_o, float* __restrict__ rays_d, float* __restrict__ pix_out) {
+  // same arithmetic as raygen_kernel (raygen.cu): float64 in the reference's operation order, one rounding to fp32
+  const double half_w = (double)img_w / 2.0, half_h = (double)img_h / 2.0;
+  const int64_t hw = (int64_t)img_w * img_h;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t id = ids[i];
+    const int v = (int)(id / hw);
+    const int rem = (int)(id - (int64_t)v * hw);
+    const int y = rem / img_w, x = rem - y * img_w;
+    const double* M = cam2world + (int64_t)v * 16;
+    const double d0 = __ddiv_rn(__dsub_rn((double)x, half_w), focal);
+    const double d1 = -__ddiv_rn(__dsub_rn((double)y, half_h), focal);
+    const double d2 = -1.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double s = __dadd_rn(__dadd_rn(__dmul_rn(d0, M[k * 4 + 0]), __dmul_rn(d1, M[k * 4 + 1])), __dmul_rn(d2, M[k * 4 + 2]));
+      rays_d[i * 3 + k] = (float)s;
+      rays_o[i * 3 + k] = (float)M[k * 4 + 3];
+    }
+    if (pix_out) pix_out[i] = pixels[id];
+  }
+}
+
+inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
+
 }  // namespace
 
 extern "C" int angio_sample_candidates(const float* weights, int64_t n_pool, uint64_t seed, float tau, int32_t capacity,
@@ -53,4 +271,60 @@ extern "C" int angio_sample_candidates(const float* weights, int64_t n_pool, uin
   if (blocks > cap) blocks = cap;
   angio::note_launch(); sample_candidates_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(weights, n_pool, seed, tau, capacity, cand_keys, cand_ids, counter);
   return angio::finish_launch("angio_sample_candidates");
+}
+
+extern "C" int64_t angio_sample_rays_workspace_bytes(int32_t capacity, int64_t n) {
+  if (capacity <= 0 || n < 0) return ANGIO_ERR_INVALID_ARG;
+  // control words + bucket counters | candidate keys | candidate ids | bucketed hashes | bucketed ids
+  return align256(16 + (3 * kMaxBuckets + 1) * 4) + align256((int64_t)capacity * 4) + align256((int64_t)capacity * 8) + align256(n * 4) +
+         align256(n * 8);
+}
+
+extern "C" int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n, uint64_t seed, float tau, int32_t capacity,
+                                 int64_t* ids_out, int32_t* status, void* workspace, int64_t workspace_bytes, void* stream) {
+  ANGIO_REQUIRE(n_pool > 0 && n > 0 && n <= n_pool && capacity >= n && tau > 0.0f && ids_out && status && workspace,
+                "angio_sample_rays: bad arguments");
+  ANGIO_REQUIRE(n <= (int64_t)1 << 24, "angio_sample_rays: at most 2^24 rays per call");
+  if (workspace_bytes < angio_sample_rays_workspace_bytes(capacity, n)) {
+    angio::set_error("angio_sample_rays: workspace too small");
+    return ANGIO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = angio::as_stream(stream);
+  char* wb = reinterpret_cast<char*>(workspace);
+  const int64_t head = align256(16 + (3 * kMaxBuckets + 1) * 4);
+  int32_t* ctl = reinterpret_cast<int32_t*>(wb);
+  uint32_t* bcount = reinterpret_cast<uint32_t*>(wb + 16);
+  uint32_t* bfill = bcount + kMaxBuckets;
+  uint32_t* bstart = bfill + kMaxBuckets;
+  wb += head;
+  float* keys = reinterpret_cast<float*>(wb); wb += align256((int64_t)capacity * 4);
+  int64_t* ids = reinterpret_cast<int64_t*>(wb); wb += align256((int64_t)capacity * 8);
+  uint32_t* tmp_hash = reinterpret_cast<uint32_t*>(wb); wb += align256(n * 4);
+  int64_t* tmp_ids = reinterpret_cast<int64_t*>(wb);
+  ANGIO_CUDA(cudaMemsetAsync(ctl, 0, 16 + 2 * kMaxBuckets * 4, st));   // counters, bucket counts and fills
+  if (int rc = angio_sample_candidates(weights, n_pool, seed, tau, capacity, keys, ids, ctl, stream)) return rc;
+  int n_buckets = 1, log2b = 0;                                        // ~32 rays per shuffle bucket
+  while (n_buckets < kMaxBuckets && (int64_t)n_buckets * 32 < n) { n_buckets <<= 1; ++log2b; }
+  int sweep_blocks = angio::blocks_for(capacity, 1024);
+  if (sweep_blocks > angio::sm_count()) sweep_blocks = angio::sm_count();
+  angio::note_launch(); select_kernel<<<1, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, status);
+  angio::note_launch(); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, seed, log2b, bcount);
+  angio::note_launch(); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, n_buckets, log2b, bcount, bfill,
+                                                                          bstart, tmp_hash, tmp_ids);
+  angio::note_launch(); bucket_sort_kernel<<<angio::blocks_for(n_buckets, 8), 256, 0, st>>>(ctl, capacity, (int32_t)n, n_buckets, bstart, tmp_hash,
+                                                                                        tmp_ids, ids_out);
+  return angio::finish_launch("angio_sample_rays");
+}
+
+extern "C" int angio_raygen_flat(const double* cam2world, const int64_t* ids, int64_t n, int32_t img_w, int32_t img_h, double focal,
+                                 const float* pixels, float* rays_o, float* rays_d, float* pix_out, void* stream) {
+  ANGIO_REQUIRE(cam2world && ids && rays_o && rays_d, "angio_raygen_flat: null pointer");
+  ANGIO_REQUIRE(n >= 0 && img_w > 0 && img_h > 0 && focal != 0.0, "angio_raygen_flat: bad sizes");
+  ANGIO_REQUIRE((pix_out == nullptr) || (pixels != nullptr), "angio_raygen_flat: pix_out needs pixels");
+  if (n == 0) return 0;
+  int blocks = angio::blocks_for(n, 256);
+  const int cap = angio::sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  angio::note_launch(); raygen_flat_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(cam2world, ids, n, img_w, img_h, focal, pixels, rays_o, rays_d, pix_out);
+  return angio::finish_launch("angio_raygen_flat");
 }

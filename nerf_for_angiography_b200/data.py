@@ -117,6 +117,8 @@ class RayPool:
         self.n_rays = self.n_views * self.img_h * self.img_w
         self._wsum = None
         self._seed_streams = {}
+        self._bufs = ops.BufferPool()
+        self.last_status = None       # device int32[2] of the last draw: [candidates, overflow flag]
 
     @property
     def device(self):
@@ -128,10 +130,10 @@ class RayPool:
         return o, d, self.pixels[int(v)].reshape(-1)
 
     @torch.no_grad()
-    def sample_ids(self, n, weights=None, generator=None):
+    def sample_ids(self, n, weights=None, generator=None, status=None):
         """Weighted sampling without replacement of n ray ids (exponential-race / Efraimidis-Spirakis keys with a
-        threshold pre-filter so only ~1.3 n candidates reach the top-k), then a random shuffle -- the reference's
-        ``DataFrame.sample(n, weights).sample(frac=1)`` (nerf/nerf_helpers.py:139)."""
+        threshold pre-filter so only ~n + 8 sqrt(n) candidates reach the exact selection), then a random shuffle -- the
+        reference's ``DataFrame.sample(n, weights).sample(frac=1)`` (nerf/nerf_helpers.py:139).  Two kernel launches, no sync."""
         N, dev = self.n_rays, self.device
         if n > N:
             raise ValueError("cannot sample more rays than the pool holds without replacement")
@@ -154,20 +156,15 @@ class RayPool:
             rng = np.random.default_rng(generator.initial_seed() if generator is not None else None)
             self._seed_streams[key] = rng
         seed = int(rng.integers(0, 2 ** 62))
-        sel, _ = ops.sample_without_replacement(n, N, wf, wsum, wsum2, seed, dev)
-        cuda_gen = generator if (generator is not None and generator.device.type == "cuda") else None
-        return sel[torch.randperm(n, device=dev, generator=cuda_gen)]
+        ids, self.last_status = ops.sample_without_replacement(n, N, wf, wsum, wsum2, seed, dev, pool=self._bufs, status=status)
+        return ids
 
     def gather(self, ids):
-        hw = self.img_h * self.img_w
-        v = (ids // hw).to(torch.int32)
-        rem = ids % hw
-        y = (rem // self.img_w).to(torch.int32)
-        x = (rem % self.img_w).to(torch.int32)
-        return ops.raygen(self.cam2world, self.img_w, self.img_h, self.focal, view_ids=v, px=x, py=y, pixels=self.pixels)
+        return ops.raygen_flat(self.cam2world, ids, self.img_w, self.img_h, self.focal, pixels=self.pixels)
 
-    def sample(self, n, weights=None, generator=None):
-        return self.gather(self.sample_ids(n, weights=weights, generator=generator))
+    def sample(self, n, weights=None, generator=None, status=None):
+        """status: optional int32[2] device tensor receiving [candidates, overflow flag] (see ops.sample_without_replacement)."""
+        return self.gather(self.sample_ids(n, weights=weights, generator=generator, status=status))
 
 
 def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0, 135.0), kind="ct", volume_res=128,

@@ -69,8 +69,10 @@ def raygen(cam2world, img_w, img_h, focal, view=0, view_ids=None, px=None, py=No
     return (o, d, pix) if pix is not None else (o, d)
 
 
-def sample_without_replacement(n, n_pool, weights, wsum, wsum2, seed, device):
-    """n ids out of n_pool, weighted, without replacement (exponential race + threshold pre-filter).  No host sync.
+def sample_without_replacement(n, n_pool, weights, wsum, wsum2, seed, device, pool=None, status=None):
+    """n ids out of n_pool, weighted, without replacement, uniformly shuffled (exponential race + threshold pre-filter + exact
+    radix select + hash-bucket shuffle).  Two kernels, no host sync.  Returns (ids int64 [n], status int32 [2]): status[1] != 0
+    means the candidate buffer overflowed / under-filled (astronomically unlikely by construction; callers that sync anyway check it).
 
     The expected number of rays with key < tau is sum_i (1 - exp(-w_i tau)), bracketed by tau*S1 - tau^2*S2/2 and tau*S1
     (S1 = sum w, S2 = sum w^2): tau is chosen from the lower bound so at least n + 8 sigma candidates are expected, the
@@ -85,29 +87,50 @@ def sample_without_replacement(n, n_pool, weights, wsum, wsum2, seed, device):
     else:
         tau = (wsum - math.sqrt(disc)) / wsum2
         capacity = min(int(n_pool), int(tau * wsum + 10.0 * math.sqrt(tau * wsum) + 64))
-    keys = torch.full((capacity,), float("inf"), dtype=torch.float32, device=device)
-    ids = torch.full((capacity,), -1, dtype=torch.int64, device=device)
-    counter = torch.zeros((1,), dtype=torch.int32, device=device)
-    _lib.check(lib.angio_sample_candidates(_p(weights), int(n_pool), int(seed) & 0xFFFFFFFFFFFFFFFF, float(tau), capacity, _p(keys),
-                                           _p(ids), _p(counter), _stream()), "angio_sample_candidates")
-    order = torch.sort(keys).indices[:n]                 # the n smallest keys (unfilled slots hold +inf)
-    return ids[order], counter
+    capacity = max(capacity, int(n))
+    wb = int(lib.angio_sample_rays_workspace_bytes(capacity, int(n)))
+    ws = pool.get("sampler_ws", wb, device) if pool is not None else torch.empty((wb,), dtype=torch.uint8, device=device)
+    ids = torch.empty((n,), dtype=torch.int64, device=device)
+    status = torch.empty((2,), dtype=torch.int32, device=device) if status is None else _chk(status, torch.int32, "status", 1)
+    _lib.check(lib.angio_sample_rays(_p(weights), int(n_pool), int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, float(tau), capacity, _p(ids),
+                                     _p(status), _p(ws), wb, _stream()), "angio_sample_rays")
+    return ids, status
+
+
+def raygen_flat(cam2world, ids, img_w, img_h, focal, pixels=None):
+    """Rays (o, d[, target pixel]) of flat ray ids (view * H * W + y * W + x): the gather that follows the sampler."""
+    lib = _lib.load()
+    cam2world = _chk(cam2world, torch.float64, "cam2world", 3)
+    ids = _chk(ids, torch.int64, "ids", 1)
+    pixels = _chk(pixels, torch.float32, "pixels", 3, allow_none=True)
+    n, dev = ids.numel(), ids.device
+    o = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    d = torch.empty((n, 3), dtype=torch.float32, device=dev)
+    pix = torch.empty((n,), dtype=torch.float32, device=dev) if pixels is not None else None
+    _lib.check(lib.angio_raygen_flat(_p(cam2world), _p(ids), n, int(img_w), int(img_h), float(focal), _p(pixels), _p(o), _p(d), _p(pix),
+                                     _stream()), "angio_raygen_flat")
+    return (o, d, pix) if pix is not None else (o, d)
 
 
 # ------------------------------------------------------------------------------------------------ marching
-def exclusive_scan(counts):
+def exclusive_scan(counts, total_out=None):
+    """offsets[n+1] (offsets[n] = total); total_out (optional int32[1] device tensor) also receives the total."""
     lib = _lib.load()
     counts = _chk(counts, torch.int32, "counts", 1)
+    total_out = _chk(total_out, torch.int32, "total_out", 1, allow_none=True)
     n = counts.numel()
     offsets = torch.empty((n + 1,), dtype=torch.int32, device=counts.device)
-    _lib.check(lib.angio_exclusive_scan_i32(_p(counts), n, _p(offsets), None, _stream()), "angio_exclusive_scan_i32")
+    _lib.check(lib.angio_exclusive_scan_i32(_p(counts), n, _p(offsets), _p(total_out), _stream()), "angio_exclusive_scan_i32")
     return offsets
 
 
-def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size):
+def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size, capacity=None, total_out=None):
     """Two-pass occupancy-grid march.  Returns (ray_idx int32 [n], t_starts [n], t_ends [n], offsets int32 [R+1]).
 
-    One host sync (reads the total sample count to size the outputs), like the reference library.
+    capacity=None: one host sync (reads the total sample count to size the outputs), like the reference library.
+    capacity=C   : NO host sync -- the sample arrays have C entries, the first offsets[R] of which are valid; C must be an
+                   upper bound (R * (ceil((far - near) / step) + 1) always is).  Downstream kernels read the count on the
+                   device (offsets[R], also written to total_out when given).
     """
     lib = _lib.load()
     rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
@@ -127,8 +150,8 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
     _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
                                      float(near_plane), float(far_plane), float(step_size), _p(t_min), _p(t_max), _p(counts),
                                      _stream()), "angio_march_count")
-    offsets = exclusive_scan(counts)
-    n = int(offsets[-1].item())
+    offsets = exclusive_scan(counts, total_out)
+    n = int(offsets[-1].item()) if capacity is None else int(capacity)
     ray_idx = torch.empty((n,), dtype=torch.int32, device=dev)
     t0 = torch.empty((n,), dtype=torch.float32, device=dev)
     t1 = torch.empty((n,), dtype=torch.float32, device=dev)
@@ -137,6 +160,12 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
                                          _p(t_min), _p(t_max), _p(offsets), _p(ray_idx), _p(t0), _p(t1), _stream()),
                    "angio_march_write")
     return ray_idx, t0, t1, offsets
+
+
+def march_capacity(n_rays, near_plane, far_plane, step_size):
+    """Upper bound of the samples `march` can emit for n_rays rays: every sample advances t by step_size inside [near, far]."""
+    import math
+    return int(n_rays) * (int(math.ceil((float(far_plane) - float(near_plane)) / float(step_size))) + 2)
 
 
 def _bin_u8(binary, resolution):
@@ -162,8 +191,13 @@ def grid_query(points, roi_aabb, resolution, binary):
 
 
 # ------------------------------------------------------------------------------------------------ visibility
-def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre):
-    """Visibility mask + compaction.  Returns (ray_idx', t_starts', t_ends', offsets', keep)."""
+def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None):
+    """Visibility mask + compaction.  Returns (ray_idx', t_starts', t_ends', offsets', keep).
+
+    alphas / t_starts / t_ends may be capacity-sized (see `march`): only the ranges named by `offsets` are touched.
+    totals (optional int32[>=2] device tensor): totals[1] receives the kept count; the single host sync of this call then
+    reads the whole tensor, so the caller gets totals[0] (e.g. the marcher's count) for free.  Returned as a python list
+    in place of `keep` when given."""
     lib = _lib.load()
     alphas = _chk(alphas, torch.float32, "alphas", 1)
     offsets = _chk(offsets, torch.int32, "offsets", 1)
@@ -174,15 +208,20 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     kept = torch.empty((R,), dtype=torch.int32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(alphas), _p(offsets), R, float(early_stop_eps), float(alpha_thre), _p(keep), _p(kept),
                                          _stream()), "angio_visibility_mask")
-    new_offsets = exclusive_scan(kept)
-    n2 = int(new_offsets[-1].item())
+    if totals is not None:
+        new_offsets = exclusive_scan(kept, totals[1:2])
+        host_totals = totals.tolist()                      # the step's one host sync
+        n2 = host_totals[1]
+    else:
+        new_offsets = exclusive_scan(kept)
+        n2 = int(new_offsets[-1].item())
     ray_idx = torch.empty((n2,), dtype=torch.int32, device=dev)
     t0 = torch.empty((n2,), dtype=torch.float32, device=dev)
     t1 = torch.empty((n2,), dtype=torch.float32, device=dev)
     if n2 > 0:
         _lib.check(lib.angio_compact_samples(_p(keep), _p(offsets), _p(new_offsets), R, _p(t_starts), _p(t_ends), _p(ray_idx), _p(t0),
                                              _p(t1), _stream()), "angio_compact_samples")
-    return ray_idx, t0, t1, new_offsets, keep
+    return ray_idx, t0, t1, new_offsets, (keep if totals is None else host_totals)
 
 
 # ------------------------------------------------------------------------------------------------ composite
@@ -252,7 +291,7 @@ def mlp_pack(desc, params, packed=None):
     return packed
 
 
-def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None, t_ends=None):
+def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None, t_ends=None, n_dev=None):
     if points is not None:
         points = _chk(points, torch.float32, "points", 2)
         if points.shape[1] != 3:
@@ -265,7 +304,8 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
         n = ray_idx.numel()
     t_starts = _chk(t_starts, torch.float32, "t_starts", 1, allow_none=points is not None)
     t_ends = _chk(t_ends, torch.float32, "t_ends", 1, allow_none=points is not None)
-    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends))
+    n_dev = _chk(n_dev, torch.int32, "n_dev", allow_none=True)
+    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(n_dev))
     return s, n
 
 

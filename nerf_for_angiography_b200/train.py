@@ -8,6 +8,7 @@ Autograd is not involved: the composite/MSE tail and the MLP backward are explic
 """
 import math
 
+import numpy as np
 import torch
 
 from . import ops
@@ -29,6 +30,7 @@ class Trainer:
         self.early_stop_eps, self.alpha_thre, self.vessel_alpha_thre = early_stop_eps, alpha_thre, vessel_alpha_thre
         o = half_extent
         self.scene_aabb = torch.tensor([-o, -o, -o, o, o, o], dtype=torch.float32, device=self.dev)   # run_nerf_acc.py:196
+        self._aabb_host = np.array([-o, -o, -o, o, o, o], dtype=np.float32)                           # host copy: no D2H per step
         self.acc_grid = OccupancyGrid(self.scene_aabb, grid_resolution, ContractionType.AABB).to(self.dev)
         self.vessel_acc_grid = OccupancyGrid(self.scene_aabb, grid_resolution, ContractionType.AABB).to(self.dev) if vessel_grid else None
         model._ensure_flat()
@@ -63,24 +65,41 @@ class Trainer:
         if self.vessel_acc_grid is not None:
             self.vessel_acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.vessel_alpha_thre, generator=self.grid_gen)
 
-    def march_and_filter(self, o, d):
-        """acc_ray_marching (run_nerf_acc.py:287): returns (ray_idx int32, t0, t1, offsets, n_prefilter)."""
+    def march_and_filter(self, o, d, totals=None):
+        """acc_ray_marching (run_nerf_acc.py:287): returns (ray_idx int32, t0, t1, offsets, n_prefilter).
+
+        bf16 path: ONE host sync per call.  The marcher writes into capacity-sized arrays and leaves its sample count on the
+        device, the visibility-pass MLP reads it there, and the only read-back (after the visibility scan, needed to size the
+        training buffers) returns every device counter of the step at once: totals = [marched, kept, sampler candidates,
+        sampler overflow flag]."""
         g = self.acc_grid
-        ray_idx, t0, t1, offsets = ops.march(o, d, self.scene_aabb, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far,
-                                             self.step_size)
+        R = o.shape[0]
+        sync_free = self.model._precision_id == ops.PREC_BF16
+        cap = ops.march_capacity(R, self.near, self.far, self.step_size) if sync_free else None
+        if sync_free and totals is None:
+            totals = torch.zeros((4,), dtype=torch.int32, device=o.device)
+        ray_idx, t0, t1, offsets = ops.march(o, d, self._aabb_host, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far,
+                                             self.step_size, capacity=cap, total_out=totals[0:1] if sync_free else None)
         n_pre = ray_idx.numel()
         if n_pre > 0:
             if self.kernel_events is not None:
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
             alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
-                                     rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+                                     rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1,
+                                     n_dev=offsets[R:R + 1] if sync_free else None)
             if self.kernel_events is not None:
                 ev1.record()
                 self.kernel_events.append((ev0, ev1))
-                self.kernel_samples.append(n_pre)
             thre = min(self.alpha_thre, g.occs_mean_host)
-            ray_idx, t0, t1, offsets, _ = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre)
+            ray_idx, t0, t1, offsets, host_totals = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre,
+                                                                          totals=totals if sync_free else None)
+            if sync_free:
+                n_pre = host_totals[0]
+                if host_totals[3] != 0:
+                    raise RuntimeError("ray sampler: candidate buffer overflow / underflow -- re-draw with a larger threshold")
+            if self.kernel_events is not None:
+                self.kernel_samples.append(n_pre)
         return ray_idx, t0, t1, offsets, n_pre
 
     def _refresh_packed(self):
@@ -94,13 +113,14 @@ class Trainer:
         m = self.model
         if self.flat.data_ptr() != m._flat.data_ptr():
             raise RuntimeError("model parameters were re-allocated after the Trainer was built")
+        totals = torch.zeros((4,), dtype=torch.int32, device=self.dev)     # [marched, kept, sampler candidates, sampler overflow]
         if rays is None:
-            o, d, target = self.pool.sample(self.n_rays, generator=self.ray_gen)
+            o, d, target = self.pool.sample(self.n_rays, generator=self.ray_gen, status=totals[2:4])
         else:
             o, d, target = rays
         self._refresh_packed()
         self.update_grids()
-        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d)
+        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d, totals)
         n_kept = ray_idx.numel()
         R = o.shape[0]
         if n_kept > 0:                                                      # run_nerf_acc.py:289

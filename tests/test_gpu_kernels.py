@@ -56,6 +56,10 @@ def test_raygen_gather_mode(A):
         assert np.array_equal(d.cpu().numpy()[sel], rd[y[sel], x[sel]].astype(np.float32))
         assert np.array_equal(o.cpu().numpy()[sel], ro[y[sel], x[sel]].astype(np.float32))
     assert np.array_equal(p.cpu().numpy(), pix[v, y, x])
+    # flat-id mode (the sampler's output feeds it directly): same rays bit for bit
+    ids = torch.from_numpy((v.astype(np.int64) * H + y) * W + x).cuda()
+    o2, d2, p2 = A.ops.raygen_flat(_dev(mats), ids, W, H, f, pixels=_dev(pix))
+    assert o2.equal(o) and d2.equal(d) and p2.equal(p)
 
 
 # ------------------------------------------------------------------------------------------------ marching
@@ -76,6 +80,13 @@ def _march_both(A, o, d, binary, res, near=1400.0, far=1600.0, n_steps=300, aabb
     tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, aabb, near, far)
     ri, ts, te, off = nerfacc_ref.march(o, d, tmin, tmax, aabb, res, binary, step)
     gi, g0, g1, goff = A.ops.march(_dev(o), _dev(d), aabb, aabb, res, _dev(binary), near, far, float(step))
+    # capacity mode (no host sync): same samples in the first offsets[R] slots, count left on the device
+    cap = A.ops.march_capacity(len(o), near, far, float(step))
+    tot = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ci, c0, c1, coff = A.ops.march(_dev(o), _dev(d), aabb, aabb, res, _dev(binary), near, far, float(step), capacity=cap, total_out=tot)
+    n_c = int(tot.item())
+    assert n_c == gi.numel() <= cap and coff.equal(goff)
+    assert ci[:n_c].equal(gi) and c0[:n_c].equal(g0) and c1[:n_c].equal(g1)
     return (ri, ts, te, off), (gi.cpu().numpy(), g0.cpu().numpy(), g1.cpu().numpy(), goff.cpu().numpy())
 
 
@@ -324,7 +335,34 @@ def test_weighted_sampling_without_replacement(A):
     # all rays requested -> a permutation of the pool
     ids = pool.sample_ids(V * H * W, generator=g)
     assert ids.sort().values.equal(torch.arange(V * H * W, device="cuda"))
+    assert pool.last_status.tolist()[1] == 0
     # uniform pool
     pool_u = RayPool(pool.cam2world, pool.pixels, 100.0, None)
     ids = pool_u.sample_ids(1000, generator=g)
     assert ids.unique().numel() == 1000
+
+
+def test_sampler_is_reproducible_and_shuffled(A):
+    """Same seed -> the same ids in the same order (the candidate pass appends with atomics, the select/shuffle pass must
+    erase that order); the order is a uniform shuffle (no correlation between position and ray id or weight)."""
+    from nerf_for_angiography_b200.data import RayPool
+    V, H, W = 8, 256, 256
+    torch.manual_seed(1)
+    w = torch.rand(V, H, W, device="cuda") + 0.05
+    pool = RayPool(torch.eye(4, dtype=torch.float64, device="cuda").repeat(V, 1, 1), torch.rand(V, H, W, device="cuda"), 100.0, w)
+    n = 8192
+    runs = []
+    for _ in range(3):
+        g = torch.Generator(device="cuda").manual_seed(11)
+        pool._seed_streams = {}
+        runs.append(pool.sample_ids(n, generator=g))
+    assert runs[0].equal(runs[1]) and runs[0].equal(runs[2])
+    ids = runs[0]
+    assert ids.unique().numel() == n and pool.last_status.tolist()[1] == 0
+    pos = torch.arange(n, device="cuda", dtype=torch.float64)
+    for other in (ids.double(), w.reshape(-1)[ids].double()):
+        c = torch.corrcoef(torch.stack([pos, other]))[0, 1]
+        assert abs(float(c)) < 0.05, float(c)                  # |corr| ~ 1/sqrt(n) = 0.011 for a uniform shuffle
+    # exactness of the selection: the sample is the n smallest keys <=> inclusion probability grows with the weight
+    heavy = w.reshape(-1)[ids].mean()
+    assert float(heavy) > float(w.mean()) * 1.15

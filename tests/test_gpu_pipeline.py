@@ -122,6 +122,10 @@ def test_mlp_bf16_ray_sample_inputs_and_alpha(A):
     assert np.abs(got - alpha).max() <= 1e-2
     got_l = model.query(A.ops.OUT_LOGIT, **kw).cpu().numpy()
     assert np.abs(got_l - logit.numpy()).max() <= 4e-2 * max(1.0, np.abs(logit.numpy()).max())
+    # device-resident sample count: capacity-sized arrays, the kernel stops at *n_dev
+    n_dev = torch.tensor([7001], dtype=torch.int32, device="cuda")
+    got_d = model.query(A.ops.OUT_ALPHA, n_dev=n_dev, **kw)
+    assert got_d[:7001].cpu().numpy().tobytes() == got[:7001].tobytes()
 
 
 # ------------------------------------------------------------------------------------------------ render_rays / training step

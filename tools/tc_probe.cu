@@ -142,6 +142,94 @@ __global__ void __launch_bounds__(128, 1) perf_kernel(int iters, int ts_mode, fl
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// issue-cadence experiments (TS mode, K = 128 per accumulation group):
+//   mode 0: one issuer, one accumulator (baseline = variant 5)      mode 1: one issuer alternating two accumulators per k-step
+//   mode 2: two issuer warps, one accumulator each                  mode 3: one issuer, accumulate flag always 0 (no RAW chain)
+//   mode 4: one issuer, N = 64 instructions                          mode 5: two issuers, N = 256, one accumulator each
+__global__ void __launch_bounds__(128, 1) cadence_kernel(int iters, int mode, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;                 // 256 rows x 128 K
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int i = threadIdx.x; i < (256 * 256) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar_mma[0], 1); mbar_init(&bar_mma[1], 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const int NN = (mode == 4) ? 64 : (mode == 5 ? 256 : 128);
+  const uint32_t idesc = make_idesc_bf16(128, NN, 0, 0);
+  const bool issuer = (lane == 0) && (warp == 0 || ((mode == 2 || mode == 5) && warp == 1));
+  long long t0 = clock64();
+  if (issuer) {
+    // accumulators: mode 5 uses [0,256) and... only 512 columns exist, A lives in the accumulator of the other warp's
+    // region tail; values are irrelevant for timing
+    const uint32_t d0 = tmem + (mode == 5 ? 0 : warp * 128);
+    const uint32_t a0 = tmem + 384 + warp * 64;
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < 8; ++k) {
+        uint32_t b_off = (k / 4) * (NN * 128) + (k % 4) * 32;
+        uint64_t db = make_smem_desc_sw128(smem_u32(sB) + b_off, 16, 1024);
+        uint32_t d = d0;
+        if (mode == 1) d = tmem + (k & 1) * 128;
+        uint32_t acc = (mode == 3) ? 0u : (uint32_t)(mode == 1 ? k > 1 : k > 0);
+        mma_ts(d, a0 + k * 8, db, idesc, acc);
+      }
+    }
+    mma_commit(&bar_mma[warp]);
+  }
+  if (warp == 0) mbar_wait(&bar_mma[0], 0);
+  if (warp == 1 && (mode == 2 || mode == 5)) mbar_wait(&bar_mma[1], 0);
+  long long t1 = clock64();
+  fence_after_sync();
+  if (lane == 0 && warp < 2 && cycles) cycles[blockIdx.x * 2 + warp] = t1 - t0;
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// drain/restart experiment: groups of G MMAs, commit, wait for completion, repeat.  Reports cycles per group measured by the
+// issuing thread: [issue of the G MMAs + commit] and [commit -> mbarrier phase observed].
+__global__ void __launch_bounds__(128, 1) drain_kernel(int iters, int G, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sB = smem;
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x / 32;
+  for (int i = threadIdx.x; i < (128 * 256) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_base_s, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+  if (threadIdx.x == 0) {
+    long long t_issue = 0, t_wait = 0;
+    for (int it = 0; it < iters; ++it) {
+      long long a = clock64();
+      for (int k = 0; k < G; ++k) {
+        uint32_t b_off = (k / 4) * (128 * 128) + (k % 4) * 32;
+        mma_ts(tmem, tmem + 384 + k * 8, make_smem_desc_sw128(smem_u32(sB) + b_off, 16, 1024), idesc, k > 0);
+      }
+      mma_commit(&bar_mma);
+      long long b = clock64();
+      mbar_wait(&bar_mma, it & 1);
+      fence_after_sync();
+      long long c = clock64();
+      t_issue += b - a; t_wait += c - b;
+    }
+    cycles[0] = t_issue; cycles[1] = t_wait;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 __global__ void __launch_bounds__(256, 1) ldtm_bw_kernel(int iters, unsigned* sink) {
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x / 32;
@@ -185,6 +273,44 @@ int main(int argc, char** argv) {
       int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0);
       printf("LDTM warps=%d: %.3f ms, %.1f GB/s per SM, %.1f B/clk/SM at %.0f MHz (nominal max clock)\n", nw, ms, bytes_per_sm / ms * 1e-6,
              bytes_per_sm / (ms * 1e-3 * khz * 1e3), khz * 1e-3);
+    }
+    return 0;
+  }
+
+  if (variant >= 10 && variant <= 15) {
+    const int mode = variant - 10, iters = 2048;
+    size_t smem = 65536 + 1024;
+    CK(cudaFuncSetAttribute(cadence_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long* dcy; CK(cudaMalloc(&dcy, sizeof(long long) * 2 * prop.multiProcessorCount));
+    for (int nblk : {1, prop.multiProcessorCount}) {
+      cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      float ms = 0;
+      for (int rep = 0; rep < 2; ++rep) {
+        CK(cudaEventRecord(e0));
+        cadence_kernel<<<nblk, 128, smem>>>(iters, mode, dcy);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+      }
+      long long cy[2]; CK(cudaMemcpy(cy, dcy, sizeof(cy), cudaMemcpyDeviceToHost));
+      const int n_issuers = (mode == 2 || mode == 5) ? 2 : 1;
+      const double n_mma = (double)iters * 8 * n_issuers;
+      printf("CADENCE mode=%d blocks=%d: %.3f ms, %.1f cycles per MMA (CTA 0, all issuers), kernel-level %.1f ns per MMA\n", mode, nblk, ms,
+             (double)cy[0] / n_mma, ms * 1e6 / n_mma);
+    }
+    return 0;
+  }
+
+  if (variant == 16) {
+    size_t smem = 32768 + 1024;
+    CK(cudaFuncSetAttribute(drain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long* dcy; CK(cudaMalloc(&dcy, sizeof(long long) * 2));
+    for (int G : {1, 2, 3, 4, 8}) {
+      const int iters = 1000;
+      drain_kernel<<<1, 128, smem>>>(iters, G, dcy);
+      CK(cudaDeviceSynchronize());
+      long long cy[2]; CK(cudaMemcpy(cy, dcy, sizeof(cy), cudaMemcpyDeviceToHost));
+      printf("DRAIN G=%d: issue+commit %.1f cycles, commit->observed %.1f cycles, total %.1f per group\n", G, (double)cy[0] / iters,
+             (double)cy[1] / iters, (double)(cy[0] + cy[1]) / iters);
     }
     return 0;
   }

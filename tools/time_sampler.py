@@ -13,3 +13,4 @@ for w in (None, torch.rand(V, H, W, device="cuda") + 0.01):
     for _ in range(20): pool.gather(ids)
     torch.cuda.synchronize(); t2 = time.perf_counter()
     print("weights" if w is not None else "uniform", f"sample_ids {(t1 - t0) / 20 * 1e3:.3f} ms  gather {(t2 - t1) / 20 * 1e3:.3f} ms  unique={ids.unique().numel()}")
+

@@ -1,0 +1,61 @@
+"""GPU timeline of a few training steps (torch.profiler / CUPTI): every kernel with its start offset, duration and the
+idle gap before it, plus the busy fraction of the step.  Diagnostic only -- not a bench number.
+
+    python tools/timeline.py [--workload config3] [--steps 2] [--start-iter 257]
+"""
+import argparse
+import os
+import sys
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import nerf_for_angiography_b200 as A  # noqa: E402
+from nerf_for_angiography_b200.data import make_dataset  # noqa: E402
+from nerf_for_angiography_b200.train import Trainer  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="config3")
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--start-iter", type=int, default=257)
+    ap.add_argument("--precision", default="bf16")
+    args = ap.parse_args()
+    w = bench.WORKLOADS[args.workload]
+    dev = torch.device("cuda", 0)
+    pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], kind="ct", volume_res=w["vol"], device=dev)
+    model = A.CPPN(bench.model_def(w, dev, args.precision)).to(dev)
+    tr = Trainer(model, pool, info["near"], info["far"], n_rays=w["rays"])
+    for _ in range(4):
+        tr.step()
+    tr.n_iter = args.start_iter
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(args.steps):
+            tr.step()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    if not evs:
+        print("no CUDA events captured")
+        return
+    t0 = evs[0].time_range.start
+    end_prev = t0
+    busy = 0.0
+    print(f"{'start_us':>10} {'dur_us':>9} {'gap_us':>8}  kernel")
+    for e in evs:
+        s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
+        gap = e.time_range.start - end_prev
+        busy += d
+        end_prev = max(end_prev, e.time_range.end)
+        print(f"{s:10.1f} {d:9.1f} {gap:8.1f}  {e.name[:90]}")
+    total = end_prev - t0
+    print(f"steps={args.steps} span={total / 1e3:.3f} ms busy={busy / 1e3:.3f} ms ({100 * busy / total:.1f}%) per-step span={total / 1e3 / args.steps:.3f} ms")
+
+
+if __name__ == "__main__":
+    main()
