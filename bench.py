@@ -227,22 +227,26 @@ def main():
     if not args.no_clocks:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tr.kernel_events, tr.kernel_samples = [], []                       # event pairs around the visibility-pass MLP launch
-    n_pre_total = n_kept_total = 0
+    tr.kernel_events, tr.kernel_totals = [], []                        # event pairs around the visibility-pass MLP launch
+    step_totals = []                                                   # device counters of every step, read after the timed region
     torch.cuda.profiler.start()                                        # ncu --profile-from-start off captures exactly the timed region
     e0.record()
     for _ in range(args.steps):
         out = tr.step()
-        n_pre_total += out["n_samples_prefilter"]
-        n_kept_total += out["n_samples"]
+        step_totals.append(out["totals"])
     e1.record()
     sync_all()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if not args.no_clocks else None
     launches = int(lib.angio_launch_count()) - launches0
+    host_totals = [t.tolist() if isinstance(t, torch.Tensor) else list(t) for t in step_totals]
+    if any(len(t) > 3 and t[3] != 0 for t in host_totals):
+        raise RuntimeError("ray sampler overflow during the timed region")
+    n_pre_total = sum(t[0] for t in host_totals)
+    n_kept_total = sum(t[1] for t in host_totals)
     kernel_ms = [a.elapsed_time(b) for a, b in tr.kernel_events]
-    kernel_n = list(tr.kernel_samples)
+    kernel_n = [(t.tolist() if isinstance(t, torch.Tensor) else list(t))[0] for t in tr.kernel_totals]
     tr.kernel_events = None
     last_loss = float(out["loss"])
 

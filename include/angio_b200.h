@@ -143,7 +143,8 @@ typedef struct angio_samples {
   const float* t_ends;    /* [n] */
   const int32_t* n_dev;   /* optional DEVICE-resident sample count: kernels process min(*n_dev, n) samples, so a marcher
                              that leaves its total on the device can feed the MLP without a host sync (n = capacity of
-                             the arrays).  Supported by the bf16 inference forward; NULL everywhere else. */
+                             the arrays; tile-image layouts of the saved activations are strided by that capacity).
+                             Supported by the bf16 (tcgen05) forward and backward; must be NULL for ANGIO_PREC_FP32. */
 } angio_samples;
 
 #define ANGIO_OUT_LOGIT 0 /* raw model output (CPPN.forward)                                   */
@@ -212,10 +213,12 @@ ANGIO_API int angio_grid_threshold(const float* occs, int64_t n_cells, float occ
 /* ------------------------------------------------------------------------------------------------
  * Optimiser.   Replaces torch.optim.Adam.step (nerf/run_nerf_acc.py:206,305-307) on the flat buffers.
  * step is 1-based.  grad_scale multiplies the gradient first (1/world_size after an all-reduce sum).
+ * active (optional, DEVICE float): when non-NULL and *active == 0 the step is skipped -- the sync-free training loop keeps
+ * its kept-sample count on the device, and an iteration without samples takes no optimiser step (nerf/run_nerf_acc.py:289).
  */
 ANGIO_API int angio_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                     float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
-                    void* stream);
+                    const float* active, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,7 +56,7 @@ PROTOTYPES = {
     "angio_grid_cell_points": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr]),
     "angio_grid_ema_update": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_i64, c_ptr]),
     "angio_grid_threshold": (c_i32, [c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
-    "angio_adam_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_ptr]),
+    "angio_adam_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_ptr, c_ptr]),
 }
 
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE = -1, -2, -3

@@ -80,8 +80,8 @@ extern "C" int angio_mlp_forward(const angio_mlp_desc* desc, const float* params
   ANGIO_REQUIRE(out_mode >= ANGIO_OUT_LOGIT && out_mode <= ANGIO_OUT_ALPHA, "angio_mlp_forward: bad out_mode");
   if (int rc = check_samples(in, "angio_mlp_forward")) return rc;
   ANGIO_REQUIRE(!(out_mode == ANGIO_OUT_ALPHA && in->n > 0 && !(in->t_starts && in->t_ends)), "angio_mlp_forward: ALPHA output needs t_starts/t_ends");
-  if (in->n_dev && (precision != ANGIO_PREC_BF16 || saved)) {
-    angio::set_error("angio_mlp_forward: a device-resident sample count (n_dev) is only supported by the bf16 inference forward");
+  if (in->n_dev && precision != ANGIO_PREC_BF16) {
+    angio::set_error("angio_mlp_forward: a device-resident sample count (n_dev) is only supported by the bf16 path");
     return ANGIO_ERR_UNSUPPORTED;
   }
   if (precision == ANGIO_PREC_FP32)
@@ -103,7 +103,7 @@ extern "C" int angio_mlp_backward(const angio_mlp_desc* desc, const float* param
   ANGIO_REQUIRE(params && grad_params, "angio_mlp_backward: null pointer");
   if (int rc = check_samples(in, "angio_mlp_backward")) return rc;
   ANGIO_REQUIRE(in->n == 0 || (saved && grad_out), "angio_mlp_backward: needs saved activations and grad_out");
-  ANGIO_REQUIRE(!in->n_dev, "angio_mlp_backward: n_dev is not supported");
+  ANGIO_REQUIRE(!in->n_dev || precision == ANGIO_PREC_BF16, "angio_mlp_backward: n_dev is only supported by the bf16 path");
   if (precision == ANGIO_PREC_FP32)
     return angio::simt_backward(L, params, *in, saved, grad_out, grad_params, workspace, workspace_bytes, angio::as_stream(stream));
   if (precision == ANGIO_PREC_BF16) {

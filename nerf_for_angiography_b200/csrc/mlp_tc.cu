@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
   int64_t n = in.n;
+  const int64_t lay_tiles = (n + kTile - 1) / kTile;                     // tile-image layout stride: capacity of the arrays
   if (in.n_dev) { const int64_t nd = *in.n_dev; n = nd < n ? nd : n; }   // device-resident count (sync-free marcher -> MLP)
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...; slot = j & 1
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
           pk[16 + 2 * jj + 1] = pack_bf16x2_relu(u3.x, u3.y);
         }
         tmem_st32(a_tmem + h * 32, pk);
-        if (TRAIN) store_row_block(saved + n_tiles * kA0Bytes + ((int64_t)l * n_tiles + tile) * kActBytes + h * 16384, row, pk);
+        if (TRAIN) store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
         wait_st();
         fence_before_sync();
         mbar_arrive(&bars.a_ready[g]);
@@ -439,7 +440,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
   __shared__ float s_coef[16][16];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
-  const int64_t n = in.n;
+  int64_t n = in.n;
+  const int64_t lay_tiles = (n + kTile - 1) / kTile;                     // tile-image layout stride (capacity)
+  if (in.n_dev) { const int64_t nd = *in.n_dev; n = nd < n ? nd : n; }
   const int64_t n_tiles = (n + kTile - 1) / kTile;
   const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   pipe_setup(bars, warp);
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
     mbar_wait(&bars.w_ready, 0);
     const float* coef = consts + (L + 2) * 128 + 4;
     const float* w_out = consts + (L + 1) * 128 + h * 64;
-    const uint8_t* act_base = saved + n_tiles * kA0Bytes + h * 16384;   // a_d block h of tile t: + ((d-1) * n_tiles + t) * 32 KB
+    const uint8_t* act_base = saved + lay_tiles * kA0Bytes + h * 16384;   // a_d block h of tile t: + ((d-1) * lay_tiles + t) * 32 KB
     uint8_t* delta_h = delta + h * 16384;
     uint32_t phase = 0;
     for (int64_t j = g; j < my_tiles; j += 2) {
@@ -510,14 +513,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
       // ---- delta_{L+1} = g * w_out * relu'(a_{L+1})   (this warp: columns [64h, 64h+64))
       {
         uint32_t a[32], pk[32];
-        load_row_block(act_base + ((int64_t)L * n_tiles + tile) * kActBytes, row, a);
+        load_row_block(act_base + ((int64_t)L * lay_tiles + tile) * kActBytes, row, a);
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float2 w2 = *reinterpret_cast<const float2*>(w_out + 2 * c);
           pk[c] = hmul2_u32(pack_bf16x2(gr * w2.x, gr * w2.y), relu_mask2(a[c]));
         }
         tmem_st32(a_tmem, pk);
-        store_row_block(delta_h + ((int64_t)L * n_tiles + tile) * kActBytes, row, pk);
+        store_row_block(delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, row, pk);
       }
       if (n_stages > 0) {
         wait_st();
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
         uint32_t r0[32], r1[32], a[32], pk[32];
         tmem_ld32(acc_tmem + h * 64, r0);
         tmem_ld32(acc_tmem + h * 64 + 32, r1);
-        load_row_block(act_base + ((int64_t)(d - 2) * n_tiles + tile) * kActBytes, row, a);   // a_{d-1}
+        load_row_block(act_base + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, a);   // a_{d-1}
         wait_ld();
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
@@ -541,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
           pk[16 + c] = hmul2_u32(pack_bf16x2(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])), relu_mask2(a[16 + c]));
         }
         tmem_st32(a_tmem, pk);
-        store_row_block(delta_h + ((int64_t)(d - 2) * n_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}
+        store_row_block(delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}
         if (st + 1 < n_stages) {
           wait_st();
           fence_before_sync();
@@ -625,7 +628,8 @@ struct __align__(8) WgBarriers {
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const uint8_t* __restrict__ saved, const uint8_t* __restrict__ delta,
-                                                                     int64_t n_tiles, int L, int G, float* __restrict__ partials) {
+                                                                     int64_t lay_tiles, const int32_t* __restrict__ n_dev, int L, int G,
+                                                                     float* __restrict__ partials) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ WgBarriers bars;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
@@ -648,9 +652,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_tc_kernel(const uint8
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = bars.tmem_base;
+  int64_t n_tiles = lay_tiles;                             // lay_tiles: layout stride (capacity); n_tiles: tiles that hold samples
+  if (n_dev) { const int64_t t = ((int64_t)*n_dev + kTile - 1) / kTile; n_tiles = t < n_tiles ? t : n_tiles; }
   const int64_t my_tiles = (n_tiles > j0) ? (n_tiles - j0 + G - 1) / G : 0;
-  const uint8_t* d_base = delta + (int64_t)(d - 1) * n_tiles * kActBytes;
-  const uint8_t* a_base = (d == 1) ? saved : saved + n_tiles * kA0Bytes + (int64_t)(d - 2) * n_tiles * kActBytes;
+  const uint8_t* d_base = delta + (int64_t)(d - 1) * lay_tiles * kActBytes;
+  const uint8_t* a_base = (d == 1) ? saved : saved + lay_tiles * kA0Bytes + (int64_t)(d - 2) * lay_tiles * kActBytes;
 
   if (warp == 0 && lane == 0) {
     // ---- producer: bulk-copy the (delta_d, a_{d-1}) tile images into the ring
@@ -742,8 +748,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 
 // output layer: dw_out[o] = sum_s g[s] a_{L+1}[s][o], db_out = sum_s g[s]; one warp per tile, block partials
 __global__ void __launch_bounds__(256) outgrad_partial_kernel(const uint8_t* __restrict__ a_last, const float* __restrict__ g, int64_t n,
-                                                              int64_t n_tiles, float* __restrict__ partials /*[gridDim.x][132]*/) {
+                                                              const int32_t* __restrict__ n_dev, float* __restrict__ partials /*[gridDim.x][132]*/) {
   __shared__ float s_acc[8][132];
+  if (n_dev) { const int64_t nd = *n_dev; n = nd < n ? nd : n; }
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -884,7 +892,7 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
   if (!make_plan(L, &P)) { set_error("tc_backward: unsupported shape"); return ANGIO_ERR_UNSUPPORTED; }
   cudaError_t ce = cudaMemsetAsync(grad_params, 0, L.total * 4, st);
   if (ce != cudaSuccess) { set_error("memset grad_params: %s", cudaGetErrorString(ce)); return (int)ce; }
-  const int64_t n = in.n;
+  const int64_t n = in.n;                      // capacity when in.n_dev is set: the kernels stop at min(*n_dev, n)
   if (n == 0) return 0;
   const int64_t need = tc_workspace_bytes(L, n, 1) - 256;
   if (!workspace || workspace_bytes < need) {
@@ -923,14 +931,14 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
     const size_t smem = 4096 + (size_t)kWgStages * 65536 + 1024;
     static size_t cached = 0;
     if (int rc = ensure_smem(mlp_wgrad_tc_kernel, smem, &cached)) return rc;
-    angio::note_launch(); mlp_wgrad_tc_kernel<<<nl * G, kWgThreads, smem, st>>>(sv, delta, n_tiles, L.n_hidden, G, wpart);
+    angio::note_launch(); mlp_wgrad_tc_kernel<<<nl * G, kWgThreads, smem, st>>>(sv, delta, n_tiles, in.n_dev, L.n_hidden, G, wpart);
     if (int rc = finish_launch("mlp_wgrad_tc_kernel")) return rc;
     angio::note_launch(); wgrad_reduce_kernel<<<dim3((kWgPartial + 255) / 256, nl), 256, 0, st>>>(wpart, G, L, P, grad_params);
   }
   // output layer
   {
     const uint8_t* a_last = sv + n_tiles * kA0Bytes + (int64_t)L.n_hidden * n_tiles * kActBytes;
-    angio::note_launch(); outgrad_partial_kernel<<<kOutgradBlocks, 256, 0, st>>>(a_last, grad_out, n, n_tiles, opart);
+    angio::note_launch(); outgrad_partial_kernel<<<kOutgradBlocks, 256, 0, st>>>(a_last, grad_out, n, in.n_dev, opart);
     const int lo = L.n_linear - 1;
     angio::note_launch(); small_reduce_kernel<<<1, 256, 0, st>>>(opart, kOutgradBlocks, 132, 129, grad_params + L.off_w[lo], 128, grad_params + L.off_b[lo]);
   }

@@ -191,13 +191,15 @@ def grid_query(points, roi_aabb, resolution, binary):
 
 
 # ------------------------------------------------------------------------------------------------ visibility
-def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None):
+def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None, capacity=None):
     """Visibility mask + compaction.  Returns (ray_idx', t_starts', t_ends', offsets', keep).
 
     alphas / t_starts / t_ends may be capacity-sized (see `march`): only the ranges named by `offsets` are touched.
-    totals (optional int32[>=2] device tensor): totals[1] receives the kept count; the single host sync of this call then
-    reads the whole tensor, so the caller gets totals[0] (e.g. the marcher's count) for free.  Returned as a python list
-    in place of `keep` when given."""
+    totals (optional int32[>=2] device tensor): totals[1] receives the kept count.
+      capacity=None: the single host sync of this call reads the whole `totals` tensor, so the caller gets totals[0] (e.g.
+                     the marcher's count) for free; the python list is returned in place of `keep`.
+      capacity=C   : NO host sync -- outputs have C entries (C >= the kept count, e.g. the marcher's capacity), the kept
+                     count stays on the device (offsets'[R] and totals[1])."""
     lib = _lib.load()
     alphas = _chk(alphas, torch.float32, "alphas", 1)
     offsets = _chk(offsets, torch.int32, "offsets", 1)
@@ -208,7 +210,11 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     kept = torch.empty((R,), dtype=torch.int32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(alphas), _p(offsets), R, float(early_stop_eps), float(alpha_thre), _p(keep), _p(kept),
                                          _stream()), "angio_visibility_mask")
-    if totals is not None:
+    host_totals = None
+    if capacity is not None:
+        new_offsets = exclusive_scan(kept, totals[1:2] if totals is not None else None)
+        n2 = int(capacity)
+    elif totals is not None:
         new_offsets = exclusive_scan(kept, totals[1:2])
         host_totals = totals.tolist()                      # the step's one host sync
         n2 = host_totals[1]
@@ -221,7 +227,7 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     if n2 > 0:
         _lib.check(lib.angio_compact_samples(_p(keep), _p(offsets), _p(new_offsets), R, _p(t_starts), _p(t_ends), _p(ray_idx), _p(t0),
                                              _p(t1), _stream()), "angio_compact_samples")
-    return ray_idx, t0, t1, new_offsets, (keep if totals is None else host_totals)
+    return ray_idx, t0, t1, new_offsets, (keep if host_totals is None else host_totals)
 
 
 # ------------------------------------------------------------------------------------------------ composite
@@ -310,7 +316,9 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
 
 
 class BufferPool:
-    """Grow-only device scratch buffers (saved activations / workspaces) so steady-state steps never hit cudaMalloc."""
+    """Grow-only device scratch buffers (saved activations / workspaces / sample arrays) so steady-state steps never hit
+    cudaMalloc.  A buffer that must grow doubles (the kept-sample count rises steadily while a model trains; a 1.3x policy
+    re-allocated multi-GB buffers every few iterations) and the old block is released first."""
 
     def __init__(self):
         self._bufs = {}
@@ -318,9 +326,23 @@ class BufferPool:
     def get(self, key, nbytes, device):
         b = self._bufs.get(key)
         if b is None or b.numel() < nbytes or b.device != device:
-            b = torch.empty((int(max(nbytes, 1) * 1.3) + 256,), dtype=torch.uint8, device=device)
+            self._bufs[key] = b = None                       # drop the old block before asking for the bigger one
+            b = torch.empty((int(max(nbytes, 1)) * 2 + 256,), dtype=torch.uint8, device=device)
             self._bufs[key] = b
         return b
+
+    def reserve(self, key, nbytes, device):
+        """Exact-size allocation up front (worst-case preallocation of the sync-free training loop)."""
+        b = self._bufs.get(key)
+        if b is None or b.numel() < nbytes or b.device != device:
+            self._bufs[key] = b = None
+            self._bufs[key] = torch.empty((int(max(nbytes, 1)) + 256,), dtype=torch.uint8, device=device)
+        return self._bufs[key]
+
+    def typed(self, key, n, dtype, device):
+        """n elements of dtype carved from the pooled buffer `key`."""
+        item = torch.empty((), dtype=dtype).element_size()
+        return self.get(key, n * item, device)[:n * item].view(dtype)
 
 
 def mlp_forward(desc, params, packed, out_mode, precision, saved=False, pool=None, **sample_kw):
@@ -402,9 +424,14 @@ def grid_threshold(occs, occ_thre, binary_u8):
 
 
 # ------------------------------------------------------------------------------------------------ optimiser
-def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, active=None):
+    """active: optional float32[1] device tensor; the step is skipped when it holds 0 (see angio_adam_step)."""
     lib = _lib.load()
-    for t, nme in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+    for t, nme in ((params, "params"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _chk(t, torch.float32, nme, 1)
+    _chk(grads, torch.float32, "grads", 1)
+    if grads.numel() < params.numel():
+        raise ValueError("grads is smaller than params")
+    active = _chk(active, torch.float32, "active", 1, allow_none=True)
     _lib.check(lib.angio_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1),
-                                   float(beta2), float(eps), int(step), float(grad_scale), _stream()), "angio_adam_step")
+                                   float(beta2), float(eps), int(step), float(grad_scale), _p(active), _stream()), "angio_adam_step")

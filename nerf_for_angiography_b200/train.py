@@ -6,20 +6,41 @@ One ``Trainer.step()`` is one reference iteration:
   -> MLP forward on the kept samples -> Beer-Lambert composite + MSE -> backward -> Adam -> lr decay.
 Autograd is not involved: the composite/MSE tail and the MLP backward are explicit kernels on flat buffers.
 """
+import ctypes
 import math
 
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 from .model.CPPN import CPPN
 from .nerfacc import ContractionType, OccupancyGrid
+
+
+class StepResult(dict):
+    """Result of Trainer.step().  `loss` is a device scalar; the sample counts live in `totals` (device int32
+    [marched, kept, sampler candidates, sampler overflow]) and are fetched -- one D2H copy -- only when
+    `n_samples_prefilter` / `n_samples` are actually read, so a training loop that does not look at them never syncs."""
+
+    def _resolve(self):
+        if "_host_totals" not in self:
+            t = dict.__getitem__(self, "totals")
+            dict.__setitem__(self, "_host_totals", t.tolist() if isinstance(t, torch.Tensor) else list(t))
+        return dict.__getitem__(self, "_host_totals")
+
+    def __getitem__(self, key):
+        if key in ("n_samples_prefilter", "n_samples") and not dict.__contains__(self, key):
+            h = self._resolve()
+            if h[3] != 0:
+                raise RuntimeError("ray sampler: candidate buffer overflow / underflow -- re-draw with a larger threshold")
+            return h[0] if key == "n_samples_prefilter" else h[1]
+        return dict.__getitem__(self, key)
 
 
 class Trainer:
     def __init__(self, model: CPPN, pool, near, far, n_rays=5625, n_steps=300, half_extent=100.0, grid_resolution=128,
                  lr=1e-4, decay_rate=0.1, decay_steps=500000, early_stop_eps=1e-2, alpha_thre=1e-4, vessel_alpha_thre=5e-2,
-                 vessel_grid=True, seed=0, process_group=None):
+                 vessel_grid=True, seed=0, process_group=None, sync_free="auto", memory_fraction=0.6):
         self.model = model
         self.pool = pool
         self.dev = pool.device
@@ -35,7 +56,8 @@ class Trainer:
         self.vessel_acc_grid = OccupancyGrid(self.scene_aabb, grid_resolution, ContractionType.AABB).to(self.dev) if vessel_grid else None
         model._ensure_flat()
         self.flat = model._flat
-        self.grad = torch.zeros_like(self.flat)
+        # one extra slot behind the gradient carries the kept-sample count through the all-reduce (Adam skips on 0)
+        self.grad = torch.zeros(self.flat.numel() + 1, dtype=torch.float32, device=self.dev)
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.packed = None
@@ -53,7 +75,30 @@ class Trainer:
         self.grid_gen = torch.Generator(device=self.dev).manual_seed(seed)
         self.last = {}
         self.kernel_events = None     # bench.py: list of (start, end) CUDA events around the visibility-pass MLP launch
-        self.kernel_samples = []
+        self.kernel_totals = []       # ... and the step's device counters (sample count of that launch = totals[0])
+        self.sync_free = self._plan_memory(sync_free, memory_fraction)
+
+    # ------------------------------------------------------------------ memory plan
+    def _plan_memory(self, mode, fraction):
+        """The sync-free loop sizes every per-sample buffer for the worst case (each ray keeps every march step) so that no
+        sample count ever has to reach the host: 12 B/sample marched + 12 B/sample kept + alphas / logits / gradients / mask
+        + the bf16 tile images of the training forward/backward.  Used when that fits in `fraction` of the free HBM (config 3:
+        ~55 GB of 180 GB); otherwise the loop reads the kept count once per step and grows its buffers geometrically."""
+        if mode is False or self.model._precision_id != ops.PREC_BF16:
+            return False
+        lib, desc, prec = _lib.load(), self.model._desc, self.model._precision_id
+        cap = ops.march_capacity(self.n_rays, self.near, self.far, self.step_size)
+        need = cap * 48 + int(lib.angio_mlp_saved_bytes(ctypes.byref(desc), cap, prec)) + \
+            int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), cap, prec, 1))
+        free, _ = torch.cuda.mem_get_info(self.dev)
+        if need > fraction * free:
+            if mode is True:
+                raise RuntimeError(f"sync-free training needs {need / 2**30:.1f} GiB of buffers, {free / 2**30:.1f} GiB are free")
+            return False
+        self.capacity = cap
+        self.pool_bufs.reserve("saved", int(lib.angio_mlp_saved_bytes(ctypes.byref(desc), cap, prec)), self.dev)
+        self.pool_bufs.reserve("bwd_ws", int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), cap, prec, 1)), self.dev)
+        return True
 
     # ------------------------------------------------------------------ pieces
     def _occ_eval(self, x):
@@ -65,21 +110,23 @@ class Trainer:
         if self.vessel_acc_grid is not None:
             self.vessel_acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.vessel_alpha_thre, generator=self.grid_gen)
 
-    def march_and_filter(self, o, d, totals=None):
+    def march_and_filter(self, o, d, totals=None, sync_free=None):
         """acc_ray_marching (run_nerf_acc.py:287): returns (ray_idx int32, t0, t1, offsets, n_prefilter).
 
-        bf16 path: ONE host sync per call.  The marcher writes into capacity-sized arrays and leaves its sample count on the
-        device, the visibility-pass MLP reads it there, and the only read-back (after the visibility scan, needed to size the
-        training buffers) returns every device counter of the step at once: totals = [marched, kept, sampler candidates,
-        sampler overflow flag]."""
+        fp32 check path: exact-size arrays, two host syncs (marched and kept counts), like the reference library.
+        bf16 path: the marcher writes into capacity-sized arrays and leaves its sample count on the device, the
+        visibility-pass MLP reads it there.  With sync_free the compaction does the same (no host sync at all; n_prefilter is
+        returned as None and all counts stay in `totals` = [marched, kept, sampler candidates, sampler overflow]); otherwise
+        ONE read-back after the visibility scan sizes the training buffers and returns every counter at once."""
         g = self.acc_grid
         R = o.shape[0]
-        sync_free = self.model._precision_id == ops.PREC_BF16
-        cap = ops.march_capacity(R, self.near, self.far, self.step_size) if sync_free else None
-        if sync_free and totals is None:
+        bf16 = self.model._precision_id == ops.PREC_BF16
+        sync_free = self.sync_free if sync_free is None else (sync_free and bf16)
+        cap = ops.march_capacity(R, self.near, self.far, self.step_size) if bf16 else None
+        if bf16 and totals is None:
             totals = torch.zeros((4,), dtype=torch.int32, device=o.device)
         ray_idx, t0, t1, offsets = ops.march(o, d, self._aabb_host, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far,
-                                             self.step_size, capacity=cap, total_out=totals[0:1] if sync_free else None)
+                                             self.step_size, capacity=cap, total_out=totals[0:1] if bf16 else None)
         n_pre = ray_idx.numel()
         if n_pre > 0:
             if self.kernel_events is not None:
@@ -87,19 +134,21 @@ class Trainer:
                 ev0.record()
             alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
                                      rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1,
-                                     n_dev=offsets[R:R + 1] if sync_free else None)
+                                     n_dev=offsets[R:R + 1] if bf16 else None)
             if self.kernel_events is not None:
                 ev1.record()
                 self.kernel_events.append((ev0, ev1))
+                self.kernel_totals.append(totals if bf16 else [n_pre])
             thre = min(self.alpha_thre, g.occs_mean_host)
             ray_idx, t0, t1, offsets, host_totals = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre,
-                                                                          totals=totals if sync_free else None)
+                                                                          totals=totals if bf16 else None,
+                                                                          capacity=cap if sync_free else None)
             if sync_free:
+                n_pre = None
+            elif bf16:
                 n_pre = host_totals[0]
                 if host_totals[3] != 0:
                     raise RuntimeError("ray sampler: candidate buffer overflow / underflow -- re-draw with a larger threshold")
-            if self.kernel_events is not None:
-                self.kernel_samples.append(n_pre)
         return ray_idx, t0, t1, offsets, n_pre
 
     def _refresh_packed(self):
@@ -108,8 +157,9 @@ class Trainer:
 
     # ------------------------------------------------------------------ one reference iteration
     def step(self, rays=None):
-        """rays: optional (o[R,3], d[R,3], target[R]) -- otherwise sampled from the pool.  Returns a dict of device
-        scalars / python ints; nothing here forces a sync beyond the two sample-count reads of the marcher."""
+        """rays: optional (o[R,3], d[R,3], target[R]) -- otherwise sampled from the pool.  Returns a StepResult: `loss` is a
+        device scalar, the sample counts are fetched lazily.  In sync-free mode nothing in here waits for the GPU (except the
+        occupancy-grid refresh every 16th iteration, which reads mean(occs))."""
         m = self.model
         if self.flat.data_ptr() != m._flat.data_ptr():
             raise RuntimeError("model parameters were re-allocated after the Trainer was built")
@@ -118,20 +168,27 @@ class Trainer:
             o, d, target = self.pool.sample(self.n_rays, generator=self.ray_gen, status=totals[2:4])
         else:
             o, d, target = rays
+        R = o.shape[0]
+        sync_free = self.sync_free and R <= self.n_rays
         self._refresh_packed()
         self.update_grids()
-        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d, totals)
-        n_kept = ray_idx.numel()
-        R = o.shape[0]
+        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d, totals, sync_free=sync_free)
+        n_kept = ray_idx.numel()                                            # sync-free: the capacity, not the count
         if n_kept > 0:                                                      # run_nerf_acc.py:289
             prec = m._precision_id
             kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+            if sync_free:
+                kw["n_dev"] = offsets[R:R + 1]
             logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
             pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world)
             ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
+            active = None
+            if sync_free:
+                self.grad[-1:].copy_(offsets[R:R + 1])                      # kept count rides behind the gradient
+                active = self.grad[-1:]
             if self.world > 1:
                 torch.distributed.all_reduce(self.grad, group=self.pg)      # sum of per-rank (1/global-batch)-scaled grads
-            ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1)
+            ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1, active=active)
             self.n_iter_adam += 1
             self.lr = self.lr0 * (self.decay_rate ** (self.n_iter / self.decay_steps))   # run_nerf_acc.py:323-328
             loss = loss_sum / R
@@ -139,7 +196,9 @@ class Trainer:
             loss = torch.full((1,), float("nan"), device=self.dev)
             pix = torch.ones(R, device=self.dev)
         self.n_iter += 1
-        self.last = dict(loss=loss, n_samples_prefilter=n_pre, n_samples=n_kept, n_rays=R, pix=pix)
+        self.last = StepResult(loss=loss, totals=totals, n_rays=R, pix=pix)
+        if not sync_free:
+            self.last["n_samples_prefilter"], self.last["n_samples"] = n_pre, n_kept
         return self.last
 
     n_iter_adam = 0
@@ -164,7 +223,7 @@ class Trainer:
     def render_view(self, v, binary_thresh=None):
         o, d, target = self.pool.rays_of_view(v)
         self._refresh_packed()
-        ray_idx, t0, t1, offsets, _ = self.march_and_filter(o, d)
+        ray_idx, t0, t1, offsets, _ = self.march_and_filter(o, d, sync_free=False)    # exact-size arrays for the eval path
         if ray_idx.numel() == 0:
             return torch.ones_like(target), target
         logits = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_LOGIT, self.model._precision_id,

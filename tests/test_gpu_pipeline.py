@@ -215,7 +215,7 @@ def test_training_step_vs_oracle_fp32(A):
     order = (["fourier_coefficients"] if pos_enc == "fourier" else []) + \
         [f"early_pts_layers.{2 * i}.{w}" for i in range(L + 1) for w in ("weight", "bias")] + ["output_linear.0.weight", "output_linear.0.bias"]
     gref = np.concatenate([params[k].grad.numpy().reshape(-1) for k in order])
-    got = tr.grad.cpu().numpy()
+    got = tr.grad[:-1].cpu().numpy()                                 # last slot: kept-sample count of the sync-free loop
     assert np.max(np.abs(got - gref)) <= 1e-4 * np.abs(gref).max(), np.max(np.abs(got - gref)) / np.abs(gref).max()
     # parameters after Adam: wherever the gradient is well above Adam's eps the update is -lr*sign(g) on both sides
     sd = model.state_dict()
@@ -223,6 +223,44 @@ def test_training_step_vs_oracle_fp32(A):
         g = params[k].grad.numpy()
         big = np.abs(g) > 1e-5
         assert np.allclose(sd[k].cpu().numpy()[big], params[k].detach().numpy()[big], rtol=0, atol=2e-6), k
+
+
+def test_sync_free_step_equals_one_sync_step(A):
+    """bf16 training step with every sample count kept on the device (capacity-sized buffers, n_dev everywhere) against the
+    same step with the kept count read back: same samples, bit-identical loss, gradients and parameters.  Also the empty
+    iteration: no samples -> no optimiser step."""
+    from nerf_for_angiography_b200.data import RayPool
+    from nerf_for_angiography_b200.train import Trainer
+    og, gg, roi, o, d = _small_scene(A)
+    p = _scaled_params(4, 128, "fourier", seed=5)
+    target = torch.from_numpy(np.random.default_rng(2).random(len(o)).astype(np.float32)).cuda()
+    rays = (torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), target)
+    res = {}
+    for mode in (False, True):
+        model = A.CPPN(_model_def(4, 128, "fourier", "bf16"))
+        model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+        model = model.to("cuda")
+        pool = RayPool(torch.eye(4, dtype=torch.float64).cuda()[None], torch.zeros(1, 2, 2).cuda(), 1.0)
+        tr = Trainer(model, pool, 1400.0, 1600.0, n_rays=len(o), vessel_grid=False, sync_free=mode)
+        assert tr.sync_free is mode
+        tr.acc_grid = gg
+        tr.n_iter = 1
+        out = tr.step(rays=rays)
+        res[mode] = (out["n_samples_prefilter"], out["n_samples"], float(out["loss"]), tr.grad[:-1].clone(), tr.flat.clone(), out["pix"].clone())
+    a, b = res[False], res[True]
+    assert a[0] == b[0] > 0 and a[1] == b[1] > 0
+    assert a[2] == b[2] and a[5].equal(b[5])                          # same samples -> bit-identical projection and loss
+    # gradients: the persistent kernels spread the tiles over a capacity-sized grid, so the fixed-order partial sums of the
+    # reductions are grouped differently -> fp32 re-association only (tolerance 1e-5 of the largest gradient entry)
+    scale = float(a[3].abs().max())
+    assert float((a[3] - b[3]).abs().max()) <= 1e-5 * scale, float((a[3] - b[3]).abs().max()) / scale
+    assert float((a[4] - b[4]).abs().max()) <= 2.1e-4            # one Adam step moves a parameter by at most lr = 1e-4
+    # empty grid: no samples anywhere -> parameters and Adam moments untouched, pixels render 1
+    empty = A.OccupancyGrid(torch.tensor(roi), 32, A.ContractionType.AABB).cuda()
+    tr.acc_grid = empty
+    before = tr.flat.clone()
+    out = tr.step(rays=rays)
+    assert out["n_samples"] == 0 and tr.flat.equal(before) and bool((out["pix"] == 1).all())
 
 
 # ------------------------------------------------------------------------------------------------ bf16 tcgen05 backward
