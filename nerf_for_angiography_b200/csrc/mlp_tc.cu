@@ -18,8 +18,11 @@
 //                  A group encodes its samples, stores the bf16 features into TMEM (tcgen05.st) as the A operand, and
 //                  after each layer's MMA pulls the fp32 accumulators back (tcgen05.ld), adds the bias (packed
 //                  f32x2), applies ReLU while packing to bf16 and stores them straight back into TMEM as the next A.
-//                  The output layer is one more MMA with N = 16.  The two groups ping-pong so the tensor core runs
-//                  one tile while the other tile is in its epilogue.
+//                  The 128 -> 1 output layer is a fp32 dot product in the last epilogue (an N = 16 MMA stage cost a full
+//                  pipeline round trip per tile).  The two groups ping-pong so the tensor core runs one tile while the
+//                  other tile is in its epilogue; a group fetches the inputs of its next tile while the current one runs,
+//                  encodes them into a separate TMEM region during the last layer's MMA and hands the tile over as soon as
+//                  the last accumulator has been drained into registers.
 //       D[128 x N] (TMEM fp32) = A[128 x K] (TMEM bf16, K-major) x W[N x K]^T (SMEM bf16, SWIZZLE_128B)
 //       Training variant: every a_d row is also written to HBM as a ready-to-MMA swizzled tile image.
 // (2) mlp_dgrad_tc_kernel same structure, running the chain delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}) with the
@@ -135,8 +138,11 @@ struct __align__(8) PipeBarriers {
   uint32_t tmem_base;
 };
 
-// Strict alternation of the two MMA-issuing warps keeps the tile slots in anti-phase (one slot in its MMA while the other
-// is in its epilogue); left alone the slots lock step and the tensor core idles during both epilogues.
+// Strict alternation of the two MMA-issuing warps.  Measured on B200 (tools/tc_probe.cu 10-16, tools/trace_fwd.py): one
+// thread streams N = 128 MMAs at the 64-cycle floor, but a drained pipe needs ~330 cycles before the first result, so a
+// slot's per-layer chain is issue 512 + pipe 330 + observe 165 + epilogue ~560 + hand-off ~190 cycles and two slots can keep
+// the tensor pipe at most ~58 % busy.  Without the token the slots convoy (3.02 ms for 17 M samples vs 2.76 ms with it); an
+// initial phase offset does not survive either way.
 struct TurnToken {
   uint32_t it = 0;
   __device__ __forceinline__ void acquire(PipeBarriers& b, int s) {
@@ -242,10 +248,19 @@ __device__ __forceinline__ uint32_t hmul2_u32(uint32_t a2, uint32_t b2) {
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// A group's A operand is ready: every lane has completed its tcgen05.st (wait::st) and fenced; one arrive per WARP -- 256
+// single-address shared-memory atomics per stage were ~250 cycles of serialised arrivals on the critical path.
+__device__ __forceinline__ void signal_a_ready(uint64_t* bar, int lane) {
+  wait_st();
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
 __device__ __forceinline__ void pipe_setup(PipeBarriers& bars, int warp) {
   if (threadIdx.x == 0) {
     mbar_init(&bars.w_ready, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads); mbar_init(&bars.acc_ready[s], 1); mbar_init(&bars.turn[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); mbar_init(&bars.turn[s], 1); }
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&bars.tmem_base, kTmemCols); tmem_relinquish(); }
@@ -265,6 +280,47 @@ __device__ __forceinline__ void load_weight_image(uint8_t* smem, const uint8_t* 
   }
 }
 
+// Epilogue body of one layer for one warp: 64 accumulator columns of this thread's row -> + bias -> ReLU -> bf16x2 words
+// (PACK) and, for the last hidden layer (LAST), this half's share of the output dot product  w_out . relu(z)  in fp32.
+template <bool LAST, bool PACK>
+__device__ __forceinline__ float bias_relu_math(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const float* __restrict__ bias,
+                                                const float* __restrict__ w_out, uint32_t (&pk)[32]) {
+  float dot0 = 0.0f, dot1 = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * jj);
+    const float4 b1 = *reinterpret_cast<const float4*>(bias + 32 + 4 * jj);
+    const float2 u0 = __fadd2_rn(make_float2(__uint_as_float(r0[4 * jj]), __uint_as_float(r0[4 * jj + 1])), make_float2(b0.x, b0.y));
+    const float2 u1 = __fadd2_rn(make_float2(__uint_as_float(r0[4 * jj + 2]), __uint_as_float(r0[4 * jj + 3])), make_float2(b0.z, b0.w));
+    const float2 u2 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * jj]), __uint_as_float(r1[4 * jj + 1])), make_float2(b1.x, b1.y));
+    const float2 u3 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * jj + 2]), __uint_as_float(r1[4 * jj + 3])), make_float2(b1.z, b1.w));
+    if (LAST) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w_out + 4 * jj);
+      const float4 w1 = *reinterpret_cast<const float4*>(w_out + 32 + 4 * jj);
+      dot0 = fmaf(fmaxf(u0.x, 0.f), w0.x, dot0); dot0 = fmaf(fmaxf(u0.y, 0.f), w0.y, dot0);
+      dot0 = fmaf(fmaxf(u1.x, 0.f), w0.z, dot0); dot0 = fmaf(fmaxf(u1.y, 0.f), w0.w, dot0);
+      dot1 = fmaf(fmaxf(u2.x, 0.f), w1.x, dot1); dot1 = fmaf(fmaxf(u2.y, 0.f), w1.y, dot1);
+      dot1 = fmaf(fmaxf(u3.x, 0.f), w1.z, dot1); dot1 = fmaf(fmaxf(u3.y, 0.f), w1.w, dot1);
+    }
+    if (PACK) {
+      pk[2 * jj] = pack_bf16x2_relu(u0.x, u0.y);
+      pk[2 * jj + 1] = pack_bf16x2_relu(u1.x, u1.y);
+      pk[16 + 2 * jj] = pack_bf16x2_relu(u2.x, u2.y);
+      pk[16 + 2 * jj + 1] = pack_bf16x2_relu(u3.x, u3.y);
+    }
+  }
+  return dot0 + dot1;
+}
+template <bool LAST, bool PACK>
+__device__ __forceinline__ float bias_relu_pack(uint32_t acc_tmem, const float* __restrict__ bias, const float* __restrict__ w_out,
+                                                uint32_t (&pk)[32]) {
+  uint32_t r0[32], r1[32];
+  tmem_ld32(acc_tmem, r0);
+  tmem_ld32(acc_tmem + 32, r1);
+  wait_ld();
+  return bias_relu_math<LAST, PACK>(r0, r1, bias, w_out, pk);
+}
+
 // ------------------------------------------------------------------------------------------------ (1) forward
 // saved (TRAIN): [a_0 images: n_tiles x 16 KB][a_1 images: n_tiles x 32 KB] ... [a_{L+1} images]
 template <int OUT_MODE, bool TRAIN>
@@ -272,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
                                                                  float* __restrict__ out, uint8_t* __restrict__ saved) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ PipeBarriers bars;
+  __shared__ float s_dot[2][kTile];                                        // output layer: column-half 1's partial dot products
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
   int64_t n = in.n;
@@ -283,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
   pipe_setup(bars, warp);
   const uint32_t tmem = bars.tmem_base;
   const float* consts = reinterpret_cast<const float*>(smem + P.off_const);
-  const int n_stages = P.n_hidden + 2;  // L+1 layers with N = 128, then the output layer with N = 16
+  const int n_stages = P.n_hidden + 1;  // L+1 layers with N = 128; the 128 -> 1 output layer runs on the CUDA cores in the last epilogue
 
   if (warp < 2) {
     // ===================== MMA issuer of slot `warp` (warp 0 also loads the weight image) =====================
@@ -291,11 +348,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     if (warp == 0 && lane == 0) load_weight_image(smem, packed, P.total_bytes, &bars.w_ready);
     mbar_wait(&bars.w_ready, 0);
     const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 0);
-    const uint32_t idesc_out = make_idesc_bf16(kTile, 16, 0, 0);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t a_tmem = tmem + 256 + s * 64;
+    const uint32_t a0_tmem = tmem + 384 + s * 32;     // encoded features of the slot's NEXT tile (own region: written ahead of time)
     const uint32_t d_tmem = tmem + s * 128;
-    const uint32_t o_tmem = tmem + 384 + s * 16;
     uint32_t phase = 0;
     // The two slots must run in anti-phase (one in its MMA while the other is in its epilogue).  Starting together they
     // lock step (their MMAs interleave in the tensor queue and finish together), so slot 1 starts half a stage late.
@@ -308,19 +364,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         fence_after_sync();
         if (lane == 0) {
           trace_event(0, s, st, (int)(j / 2));
-          if (st < n_stages - 1) {
-            const int ksteps = (st == 0) ? P.k0_pad / 16 : kH / 16;
-            const uint32_t wbase = smem_base + w_offset(st);
-            for (int k = 0; k < ksteps; ++k) {
-              mma_ts(d_tmem, a_tmem + k * 8, make_smem_desc_sw128(wbase + (k / 4) * 16384 + (k % 4) * 32, 16, 1024), idesc, k > 0);
-              if (k == 0) mbar_arrive(&bars.turn[1 - s]);   // pass the issue token early: the other slot's start-up overlaps our MMAs
-            }
-          } else {
-            const uint32_t wbase = smem_base + P.off_wout;
-            for (int k = 0; k < kH / 16; ++k) {
-              mma_ts(o_tmem, a_tmem + k * 8, make_smem_desc_sw128(wbase + (k / 4) * 2048 + (k % 4) * 32, 16, 1024), idesc_out, k > 0);
-              if (k == 0) mbar_arrive(&bars.turn[1 - s]);
-            }
+          const int ksteps = (st == 0) ? P.k0_pad / 16 : kH / 16;
+          const uint32_t wbase = smem_base + w_offset(st);
+          const uint32_t a_src = (st == 0) ? a0_tmem : a_tmem;
+          for (int k = 0; k < ksteps; ++k) {
+            mma_ts(d_tmem, a_src + k * 8, make_smem_desc_sw128(wbase + (k / 4) * 16384 + (k % 4) * 32, 16, 1024), idesc, k > 0);
+            if (k == 0) mbar_arrive(&bars.turn[1 - s]);   // pass the issue token early: the other slot's start-up overlaps our MMAs
           }
           mma_commit(&bars.acc_ready[s]);
           trace_event(1, s, st, (int)(j / 2));
@@ -343,85 +392,104 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t acc_tmem = tmem + g * 128 + lane_off + h * 64;
     const uint32_t a_tmem = tmem + 256 + g * 64 + lane_off;
-    const uint32_t oacc_tmem = tmem + 384 + g * 16 + lane_off;
+    const uint32_t a0_tmem = tmem + 384 + g * 32 + lane_off;
     mbar_wait(&bars.w_ready, 0);                  // biases / coefficients live in the packed image
     const float* coef = consts + (P.n_hidden + 2) * 128 + 4;
     const float b_out = consts[(P.n_hidden + 2) * 128];
+    const float* w_out = consts + (P.n_hidden + 1) * 128 + h * 64;   // fp32 output weights of this warp's columns
+    const int pair_bar = 1 + g * 4 + q;           // named barrier shared by the two column-half warps of this row quadrant
     const int nb = 3 * P.basis;
     uint32_t phase = 0;
+    // Software pipeline over this group's tiles: the inputs of tile j+2 (two dependent global loads: ray id -> origin /
+    // direction) are fetched while tile j runs its layers, and tile j+2 is encoded and handed to the tensor core BEFORE
+    // tile j's output is exchanged and stored, so the slot's pipeline never waits on global memory between tiles.
+    auto fetch = [&](int64_t jt, float (&xx)[3], float& dtt, bool& vv) {
+      const int64_t ii = (blockIdx.x + jt * gridDim.x) * kTile + row;
+      vv = (jt < my_tiles) && (ii < n);
+      xx[0] = xx[1] = xx[2] = 0.f;
+      dtt = 0.f;
+      if (vv) {
+        angio::sample_position(in, ii, xx);
+        if (OUT_MODE == ANGIO_OUT_ALPHA) dtt = in.t_ends[ii] - in.t_starts[ii];
+      }
+    };
+    // features of tile jt: the two halves split the 8-column chunks of a_0 (chunk c8 belongs to half c8 & 1)
+    // The features live in their own TMEM region (a0), so the NEXT tile is encoded while the tensor core runs the current
+    // tile's last layer -- off the slot's critical path.
+    auto encode = [&](int64_t jt, const float (&xx)[3]) {
+      const int64_t tl = blockIdx.x + jt * gridDim.x;
+      uint8_t* a0_row = TRAIN ? saved + tl * kA0Bytes + row * 128 : nullptr;
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        if ((c8 & 1) == h && c8 * 16 < P.k0_pad) {
+          uint32_t v8[8];
+          encode_feature_chunk(xx, coef, nb, c8, v8);
+          tmem_st8(a0_tmem + c8 * 8, v8);
+          if (TRAIN) {
+            *reinterpret_cast<uint4*>(a0_row + (((2 * c8) ^ (row & 7)) << 4)) = make_uint4(v8[0], v8[1], v8[2], v8[3]);
+            *reinterpret_cast<uint4*>(a0_row + (((2 * c8 + 1) ^ (row & 7)) << 4)) = make_uint4(v8[4], v8[5], v8[6], v8[7]);
+          }
+        } else if (TRAIN && (c8 & 1) == h) {
+          *reinterpret_cast<uint4*>(a0_row + (((2 * c8) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a0_row + (((2 * c8 + 1) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    };
+    float xn[3], dtn;
+    bool vn;
+    fetch(g, xn, dtn, vn);
+    if (g < my_tiles) { encode(g, xn); signal_a_ready(&bars.a_ready[g], lane); }
     for (int64_t j = g; j < my_tiles; j += 2) {
       const int64_t tile = blockIdx.x + j * gridDim.x;
       const int64_t i = tile * kTile + row;
-      const bool valid = i < n;
-      float x[3] = {0.f, 0.f, 0.f};
-      float dt = 0.f;
-      if (valid) {
-        angio::sample_position(in, i, x);
-        if (OUT_MODE == ANGIO_OUT_ALPHA) dt = in.t_ends[i] - in.t_starts[i];
-      }
-      // ---- features: the two halves split the 8-column chunks of a_0 (chunk c8 belongs to half c8 & 1)
-      {
-        uint8_t* a0_row = TRAIN ? saved + tile * kA0Bytes + row * 128 : nullptr;
-#pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {
-          if ((c8 & 1) == h && c8 * 16 < P.k0_pad) {
-            uint32_t v8[8];
-            encode_feature_chunk(x, coef, nb, c8, v8);
-            tmem_st8(a_tmem + c8 * 8, v8);
-            if (TRAIN) {
-              *reinterpret_cast<uint4*>(a0_row + (((2 * c8) ^ (row & 7)) << 4)) = make_uint4(v8[0], v8[1], v8[2], v8[3]);
-              *reinterpret_cast<uint4*>(a0_row + (((2 * c8 + 1) ^ (row & 7)) << 4)) = make_uint4(v8[4], v8[5], v8[6], v8[7]);
-            }
-          } else if (TRAIN && (c8 & 1) == h) {
-            *reinterpret_cast<uint4*>(a0_row + (((2 * c8) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a0_row + (((2 * c8 + 1) ^ (row & 7)) << 4)) = make_uint4(0, 0, 0, 0);
-          }
-        }
-      }
-      wait_st();
-      fence_before_sync();
-      mbar_arrive(&bars.a_ready[g]);
+      const bool valid = vn;
+      const float dt = dtn;
+      fetch(j + 2, xn, dtn, vn);                  // in flight during this tile's layers
       // ---- hidden layers: acc + bias -> relu -> bf16 -> next A operand (this warp: columns [64h, 64h+64))
-      for (int l = 0; l <= P.n_hidden; ++l) {
+      for (int l = 0; l < P.n_hidden; ++l) {
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(2, g, l, (int)(j / 2));
-        const float* bias = consts + l * 128 + h * 64;
-        uint32_t r0[32], r1[32];
+        uint32_t pk[32];
+        bias_relu_pack<false, true>(acc_tmem, consts + l * 128 + h * 64, nullptr, pk);
+        tmem_st32(a_tmem + h * 32, pk);
+        if (TRAIN) store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+        signal_a_ready(&bars.a_ready[g], lane);
+        if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, l, (int)(j / 2));
+      }
+      // ---- last hidden layer + output layer: logit = w_out . relu(z_{L+1}) + b_out on the CUDA cores, in fp32 before the
+      //      bf16 rounding (an N = 16 MMA stage for one useful column cost a full pipeline round trip per tile)
+      {
+        const int l = P.n_hidden;
+        const bool more = j + 2 < my_tiles;
+        if (more && l > 0) encode(j + 2, xn);     // stage 0 of this tile is long done: its feature region is free
+        mbar_wait(&bars.acc_ready[g], phase);
+        phase ^= 1;
+        fence_after_sync();
+        if (lane == 0 && (warp - 2) % 8 == 0) trace_event(2, g, l, (int)(j / 2));
+        uint32_t r0[32], r1[32], pk[32];
         tmem_ld32(acc_tmem, r0);
         tmem_ld32(acc_tmem + 32, r1);
         wait_ld();
-        uint32_t pk[32];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * jj);
-          const float4 b1 = *reinterpret_cast<const float4*>(bias + 32 + 4 * jj);
-          const float2 u0 = __fadd2_rn(make_float2(__uint_as_float(r0[4 * jj]), __uint_as_float(r0[4 * jj + 1])), make_float2(b0.x, b0.y));
-          const float2 u1 = __fadd2_rn(make_float2(__uint_as_float(r0[4 * jj + 2]), __uint_as_float(r0[4 * jj + 3])), make_float2(b0.z, b0.w));
-          const float2 u2 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * jj]), __uint_as_float(r1[4 * jj + 1])), make_float2(b1.x, b1.y));
-          const float2 u3 = __fadd2_rn(make_float2(__uint_as_float(r1[4 * jj + 2]), __uint_as_float(r1[4 * jj + 3])), make_float2(b1.z, b1.w));
-          pk[2 * jj] = pack_bf16x2_relu(u0.x, u0.y);
-          pk[2 * jj + 1] = pack_bf16x2_relu(u1.x, u1.y);
-          pk[16 + 2 * jj] = pack_bf16x2_relu(u2.x, u2.y);
-          pk[16 + 2 * jj + 1] = pack_bf16x2_relu(u3.x, u3.y);
+        // the accumulator is in registers: hand the slot's next tile to the tensor core BEFORE doing this tile's last math
+        if (more) {
+          if (l == 0) encode(j + 2, xn);
+          signal_a_ready(&bars.a_ready[g], lane);
         }
-        tmem_st32(a_tmem + h * 32, pk);
+        if (lane == 0 && (warp - 2) % 8 == 0) trace_event(2, g, 6, (int)(j / 2));
+        const float dot = bias_relu_math<true, TRAIN>(r0, r1, consts + l * 128 + h * 64, w_out, pk);
+        if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, 6, (int)(j / 2));
         if (TRAIN) store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
-        wait_st();
-        fence_before_sync();
-        mbar_arrive(&bars.a_ready[g]);
+        // the h = 1 warp hands its half of the dot product to the h = 0 warp of the same row quadrant
+        if (h == 1) {
+          s_dot[g][row] = dot;
+          asm volatile("bar.arrive %0, 64;" ::"r"(pair_bar) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          if (valid) out[i] = out_transform<OUT_MODE>(dot + s_dot[g][row] + b_out, dt);
+        }
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, l, (int)(j / 2));
-      }
-      // ---- output layer accumulator: column 0 of the N = 16 MMA (read by the h = 0 warps)
-      mbar_wait(&bars.acc_ready[g], phase);
-      phase ^= 1;
-      fence_after_sync();
-      if (h == 0) {
-        uint32_t o;
-        tmem_ld1(oacc_tmem, o);
-        wait_ld();
-        if (valid) out[i] = out_transform<OUT_MODE>(__uint_as_float(o) + b_out, dt);
       }
     }
   }
@@ -523,9 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
         store_row_block(delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, row, pk);
       }
       if (n_stages > 0) {
-        wait_st();
-        fence_before_sync();
-        mbar_arrive(&bars.a_ready[g]);
+        signal_a_ready(&bars.a_ready[g], lane);
       }
       // ---- hidden chain: delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}),  d = L+1 .. 2
       for (int st = 0; st < L; ++st) {
@@ -546,9 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
         tmem_st32(a_tmem, pk);
         store_row_block(delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}
         if (st + 1 < n_stages) {
-          wait_st();
-          fence_before_sync();
-          mbar_arrive(&bars.a_ready[g]);
+          signal_a_ready(&bars.a_ready[g], lane);
         }
       }
       // ---- feature gradient (delta_1 W_0) -> Fourier-coefficient gradient; half h reads feature columns [32h, 32h+32)

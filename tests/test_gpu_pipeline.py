@@ -249,7 +249,7 @@ def test_sync_free_step_equals_one_sync_step(A):
         res[mode] = (out["n_samples_prefilter"], out["n_samples"], float(out["loss"]), tr.grad[:-1].clone(), tr.flat.clone(), out["pix"].clone())
     a, b = res[False], res[True]
     assert a[0] == b[0] > 0 and a[1] == b[1] > 0
-    assert a[2] == b[2] and a[5].equal(b[5])                          # same samples -> bit-identical projection and loss
+    assert a[5].equal(b[5]) and np.isclose(a[2], b[2], rtol=1e-6)     # same samples -> bit-identical projection (the loss sum uses float atomics)
     # gradients: the persistent kernels spread the tiles over a capacity-sized grid, so the fixed-order partial sums of the
     # reductions are grouped differently -> fp32 re-association only (tolerance 1e-5 of the largest gradient entry)
     scale = float(a[3].abs().max())

@@ -24,4 +24,5 @@ rec.sort()
 t0 = rec[0][0]
 for t, k, s, st, r in rec:
     if 2 <= r <= 4:
-        print(f"{t - t0:8d}  round{r} slot{s} stage{st}  {names[k]}")
+        nm = names[k] if st < 6 else {2: "EPI: acc drained, next tile signalled", 3: "EPI: last-layer math done"}[k]
+        print(f"{t - t0:8d}  round{r} slot{s} stage{st}  {nm}")
