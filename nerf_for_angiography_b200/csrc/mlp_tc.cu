@@ -51,6 +51,7 @@ constexpr int kTmemCols = 512;
 constexpr float kTwoPi = 6.2831855f;
 constexpr int kA0Bytes = 16384;    // a_0 tile image: [128 rows x 64 cols] bf16
 constexpr int kActBytes = 32768;   // a_d / delta_d tile image: two [128 x 64] blocks
+constexpr int kMaskBytes = 2048;   // ReLU bit mask of one a_d tile: [128 rows][4 x 32 bits]
 
 struct TcPlan {
   int n_hidden;     // L: number of 128x128 layers
@@ -172,30 +173,6 @@ __device__ __forceinline__ float out_transform(float logit, float dt) {
   return 1.0f - __expf(-s * dt);
 }
 
-// encoded features of one sample as 32 bf16x2 words (K = 64): every index is static
-__device__ __forceinline__ void encode_features(const float x[3], const float* __restrict__ coef, int nb, uint32_t (&pk)[32]) {
-#pragma unroll
-  for (int c = 0; c < 32; ++c) pk[c] = 0u;
-  float hi[3], lo[3];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    hi[c] = __bfloat162float(__float2bfloat16_rn(x[c]));
-    lo[c] = x[c] - hi[c];
-  }
-  pk[0] = pack_bf16x2(hi[0], hi[1]);
-  pk[1] = pack_bf16x2(hi[2], lo[0]);
-  pk[2] = pack_bf16x2(lo[1], lo[2]);
-#pragma unroll
-  for (int jf = 0; jf < 29; ++jf) {  // up to 29 (sin, cos) pairs fit k0_pad <= 64
-    if (jf < nb) {
-      const float a = __fmul_rn(__fmul_rn(kTwoPi, x[jf % 3]), coef[jf]);
-      float sn, cs;
-      sincos_reduced(a, sn, cs);
-      pk[3 + jf] = pack_bf16x2(sn, cs);
-    }
-  }
-}
-
 // 8 consecutive bf16x2 words (16 K columns) of the encoded features: chunk c8 covers words [8 c8, 8 c8 + 8)
 // word 0..2 = x hi/lo, word 3+j = (sin_j, cos_j); all indices static after unrolling
 __device__ __forceinline__ void encode_feature_chunk(const float x[3], const float* __restrict__ coef, int nb, int c8, uint32_t (&v)[8]) {
@@ -228,24 +205,20 @@ __device__ __forceinline__ void store_row_block(uint8_t* __restrict__ block, int
     *reinterpret_cast<uint4*>(base + ((c ^ (row & 7)) << 4)) = v;
   }
 }
-__device__ __forceinline__ void load_row_block(const uint8_t* __restrict__ block, int row, uint32_t (&pk)[32]) {
-  const uint8_t* base = block + row * 128;
+// ReLU bit masks: the training forward leaves, next to every activation tile image, one bit per element (a > 0), 16 bytes
+// per row instead of 256, so the data-gradient chain never re-reads the activations (1.2 KB/sample of HBM reads saved).
+// 16 consecutive bf16x2 words -> 32 bits: bit k = low element of word k, bit 16 + k = high element.  Post-ReLU values are
+// >= +0, so adding 0x7FFF to a 16-bit half sets its top bit exactly when the half is non-zero (no carry between halves).
+__device__ __forceinline__ uint32_t relu_bits16(const uint32_t* w) {
+  uint32_t m = 0;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + ((c ^ (row & 7)) << 4)));
-    pk[4 * c] = v.x; pk[4 * c + 1] = v.y; pk[4 * c + 2] = v.z; pk[4 * c + 3] = v.w;
-  }
+  for (int k = 0; k < 16; ++k) m |= ((w[k] + 0x7FFF7FFFu) & 0x80008000u) >> (15 - k);
+  return m;
 }
-
-// bf16x2 word -> bf16x2 mask (1.0 where the element is non-zero)
-__device__ __forceinline__ uint32_t relu_mask2(uint32_t a2) {
-  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&a2);
-  const __nv_bfloat162 m = __hne2(a, __float2bfloat162_rn(0.0f));
-  return *reinterpret_cast<const uint32_t*>(&m);
-}
-__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a2, uint32_t b2) {
-  const __nv_bfloat162 r = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&a2), *reinterpret_cast<const __nv_bfloat162*>(&b2));
-  return *reinterpret_cast<const uint32_t*>(&r);
+// AND-mask for bf16x2 word k: 0xFFFF per element whose bit is set
+__device__ __forceinline__ uint32_t relu_word_mask(uint32_t m, int k) {
+  const uint32_t b = (m >> k) & 0x00010001u;
+  return (b << 16) - b;
 }
 
 // A group's A operand is ready: every lane has completed its tcgen05.st (wait::st) and fenced; one arrive per WARP -- 256
@@ -322,7 +295,7 @@ __device__ __forceinline__ float bias_relu_pack(uint32_t acc_tmem, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ (1) forward
-// saved (TRAIN): [a_0 images: n_tiles x 16 KB][a_1 images: n_tiles x 32 KB] ... [a_{L+1} images]
+// saved (TRAIN): [a_0 images: n_tiles x 16 KB][a_1 images: n_tiles x 32 KB] ... [a_{L+1} images][ReLU bit masks of a_1 .. a_{L+1}: n_tiles x 2 KB each]
 template <int OUT_MODE, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
                                                                  float* __restrict__ out, uint8_t* __restrict__ saved) {
@@ -398,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     const float b_out = consts[(P.n_hidden + 2) * 128];
     const float* w_out = consts + (P.n_hidden + 1) * 128 + h * 64;   // fp32 output weights of this warp's columns
     const int pair_bar = 1 + g * 4 + q;           // named barrier shared by the two column-half warps of this row quadrant
+    uint8_t* mask_base = TRAIN ? saved + lay_tiles * kA0Bytes + (int64_t)(P.n_hidden + 1) * lay_tiles * kActBytes : nullptr;
     const int nb = 3 * P.basis;
     uint32_t phase = 0;
     // Software pipeline over this group's tiles: the inputs of tile j+2 (two dependent global loads: ray id -> origin /
@@ -454,7 +428,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         uint32_t pk[32];
         bias_relu_pack<false, true>(acc_tmem, consts + l * 128 + h * 64, nullptr, pk);
         tmem_st32(a_tmem + h * 32, pk);
-        if (TRAIN) store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+        if (TRAIN) {
+          store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+          *reinterpret_cast<uint2*>(mask_base + (((int64_t)l * lay_tiles + tile) * kTile + row) * 16 + h * 8) =
+              make_uint2(relu_bits16(pk), relu_bits16(pk + 16));
+        }
         signal_a_ready(&bars.a_ready[g], lane);
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, l, (int)(j / 2));
       }
@@ -480,7 +458,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(2, g, 6, (int)(j / 2));
         const float dot = bias_relu_math<true, TRAIN>(r0, r1, consts + l * 128 + h * 64, w_out, pk);
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, 6, (int)(j / 2));
-        if (TRAIN) store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+        if (TRAIN) {
+          store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+          *reinterpret_cast<uint2*>(mask_base + (((int64_t)l * lay_tiles + tile) * kTile + row) * 16 + h * 8) =
+              make_uint2(relu_bits16(pk), relu_bits16(pk + 16));
+        }
         // the h = 1 warp hands its half of the dot product to the h = 0 warp of the same row quadrant
         if (h == 1) {
           s_dot[g][row] = dot;
@@ -570,7 +552,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
     mbar_wait(&bars.w_ready, 0);
     const float* coef = consts + (L + 2) * 128 + 4;
     const float* w_out = consts + (L + 1) * 128 + h * 64;
-    const uint8_t* act_base = saved + lay_tiles * kA0Bytes + h * 16384;   // a_d block h of tile t: + ((d-1) * lay_tiles + t) * 32 KB
+    // ReLU bits of a_d (d >= 1), row r, column half h: mask_base + (((d-1) * lay_tiles + tile) * 128 + r) * 16 + 8 h
+    const uint8_t* mask_base = saved + lay_tiles * kA0Bytes + (int64_t)(L + 1) * lay_tiles * kActBytes + row * 16 + h * 8;
     uint8_t* delta_h = delta + h * 16384;
     uint32_t phase = 0;
     for (int64_t j = g; j < my_tiles; j += 2) {
@@ -579,13 +562,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
       const bool valid = i < n;
       const float gr = valid ? grad_out[i] : 0.0f;
       // ---- delta_{L+1} = g * w_out * relu'(a_{L+1})   (this warp: columns [64h, 64h+64))
+      uint2 mk = __ldg(reinterpret_cast<const uint2*>(mask_base + ((int64_t)L * lay_tiles + tile) * (kTile * 16)));
       {
-        uint32_t a[32], pk[32];
-        load_row_block(act_base + ((int64_t)L * lay_tiles + tile) * kActBytes, row, a);
+        uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float2 w2 = *reinterpret_cast<const float2*>(w_out + 2 * c);
-          pk[c] = hmul2_u32(pack_bf16x2(gr * w2.x, gr * w2.y), relu_mask2(a[c]));
+          pk[c] = pack_bf16x2(gr * w2.x, gr * w2.y) & relu_word_mask(c < 16 ? mk.x : mk.y, c & 15);
         }
         tmem_st32(a_tmem, pk);
         store_row_block(delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, row, pk);
@@ -596,18 +579,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
       // ---- hidden chain: delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}),  d = L+1 .. 2
       for (int st = 0; st < L; ++st) {
         const int d = L + 1 - st;            // consumed delta index; produces delta_{d-1}
+        mk = __ldg(reinterpret_cast<const uint2*>(mask_base + ((int64_t)(d - 2) * lay_tiles + tile) * (kTile * 16)));   // a_{d-1} > 0, in flight during the MMA
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
-        uint32_t r0[32], r1[32], a[32], pk[32];
+        uint32_t r0[32], r1[32], pk[32];
         tmem_ld32(acc_tmem + h * 64, r0);
         tmem_ld32(acc_tmem + h * 64 + 32, r1);
-        load_row_block(act_base + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, a);   // a_{d-1}
         wait_ld();
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          pk[c] = hmul2_u32(pack_bf16x2(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])), relu_mask2(a[c]));
-          pk[16 + c] = hmul2_u32(pack_bf16x2(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])), relu_mask2(a[16 + c]));
+          pk[c] = pack_bf16x2(__uint_as_float(r0[2 * c]), __uint_as_float(r0[2 * c + 1])) & relu_word_mask(mk.x, c);
+          pk[16 + c] = pack_bf16x2(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])) & relu_word_mask(mk.y, c);
         }
         tmem_st32(a_tmem, pk);
         store_row_block(delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}
@@ -810,54 +793,70 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
-// output layer: dw_out[o] = sum_s g[s] a_{L+1}[s][o], db_out = sum_s g[s]; one warp per tile, block partials
+// output layer: dw_out[o] = sum_s g[s] a_{L+1}[s][o], db_out = sum_s g[s].  HBM-bound stream over the a_{L+1} tile images
+// (256 B/sample): thread = (16-byte chunk of the row, group of 8 rows), eight independent 16-byte loads in flight per thread,
+// per-thread register accumulators over the CTA's tiles, one fixed-order reduction per CTA at the end.
 __global__ void __launch_bounds__(256) outgrad_partial_kernel(const uint8_t* __restrict__ a_last, const float* __restrict__ g, int64_t n,
                                                               const int32_t* __restrict__ n_dev, float* __restrict__ partials /*[gridDim.x][132]*/) {
-  __shared__ float s_acc[8][132];
+  __shared__ float s_acc[16][132];
   if (n_dev) { const int64_t nd = *n_dev; n = nd < n ? nd : n; }
   const int64_t n_tiles = (n + kTile - 1) / kTile;
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
-  const int lane = threadIdx.x % 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int cidx = threadIdx.x % 16;            // logical 16-byte chunk: columns [8 cidx, 8 cidx + 8)
+  const int rg = threadIdx.x / 16;              // rows rg, rg + 16, ..., rg + 112
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float gsum = 0.0f;
-  for (int64_t tile = blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
-    const uint8_t* img = a_last + tile * kActBytes;
-    for (int r = 0; r < kTile; ++r) {
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint8_t* img = a_last + tile * kActBytes + (cidx / 8) * 16384;
+    uint4 v[8];
+    float gv[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = rg + 16 * k;
       const int64_t i = tile * kTile + r;
-      if (i >= n) break;
-      const float gv = g[i];
-      // lane handles columns 4*lane .. 4*lane+3 (8 bytes inside the swizzled row)
-      const int col = 4 * lane;
-      const uint8_t* p = img + (col / 64) * 16384 + sw128_offset(r, col % 64);
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-      const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
-      const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
-      acc[0] = fmaf(gv, f0.x, acc[0]); acc[1] = fmaf(gv, f0.y, acc[1]);
-      acc[2] = fmaf(gv, f1.x, acc[2]); acc[3] = fmaf(gv, f1.y, acc[3]);
-      if (lane == 0) gsum += gv;
+      v[k] = __ldg(reinterpret_cast<const uint4*>(img + r * 128 + (((cidx % 8) ^ (r & 7)) << 4)));
+      gv[k] = (i < n) ? g[i] : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[e]));
+        acc[2 * e] = fmaf(gv[k], f.x, acc[2 * e]);
+        acc[2 * e + 1] = fmaf(gv[k], f.y, acc[2 * e + 1]);
+      }
+      gsum += gv[k];
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) s_acc[warp][4 * lane + c] = acc[c];
-  if (lane == 0) s_acc[warp][128] = gsum;
+  for (int e = 0; e < 8; ++e) s_acc[rg][cidx * 8 + e] = acc[e];
+  if (cidx == 0) s_acc[rg][128] = gsum;
   __syncthreads();
   if (threadIdx.x < 129) {
     float v = 0.0f;
-    for (int wv = 0; wv < 8; ++wv) v += s_acc[wv][threadIdx.x];
+    for (int r = 0; r < 16; ++r) v += s_acc[r][threadIdx.x];
     partials[(int64_t)blockIdx.x * 132 + threadIdx.x] = v;
   }
 }
-__global__ void __launch_bounds__(256) small_reduce_kernel(const float* __restrict__ partials, int n_part, int stride, int len,
+// out[e] = sum_p partials[p][e] for e < len: one CTA per element, fixed-order (deterministic) tree over the partials
+__global__ void __launch_bounds__(128) small_reduce_kernel(const float* __restrict__ partials, int n_part, int stride, int len,
                                                            float* __restrict__ out0, int split, float* __restrict__ out1) {
-  const int e = threadIdx.x;
+  __shared__ float s_v[128];
+  const int e = blockIdx.x;
   if (e >= len) return;
   float v = 0.0f;
-  for (int p = 0; p < n_part; ++p) v += partials[(int64_t)p * stride + e];
-  if (e < split) out0[e] = v; else out1[e - split] = v;
+  for (int p = threadIdx.x; p < n_part; p += 128) v += partials[(int64_t)p * stride + e];
+  s_v[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_v[threadIdx.x] += s_v[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { if (e < split) out0[e] = s_v[0]; else out1[e - split] = s_v[0]; }
 }
 
 inline int64_t align256(int64_t b) { return (b + 255) / 256 * 256; }
-constexpr int kOutgradBlocks = 296;
+constexpr int kOutgradBlocks = 592;
 
 }  // namespace
 
@@ -892,7 +891,7 @@ int64_t tc_workspace_bytes(const MlpLayout& L, int64_t n, int training) {
 }
 int64_t tc_saved_bytes(const MlpLayout& L, int64_t n) {
   const int64_t n_tiles = (n + kTile - 1) / kTile;
-  return n_tiles * (kA0Bytes + (int64_t)(L.n_hidden + 1) * kActBytes) + 256;
+  return n_tiles * (kA0Bytes + (int64_t)(L.n_hidden + 1) * (kActBytes + kMaskBytes)) + 256;
 }
 
 int tc_pack_weights(const MlpLayout& L, const float* params, void* packed, cudaStream_t st) {
@@ -987,7 +986,7 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
     angio::note_launch(); mlp_dgrad_tc_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, sv, grad_out, delta, cpart);
     if (int rc = finish_launch("mlp_dgrad_tc_kernel")) return rc;
     if (L.enc) {
-      angio::note_launch(); small_reduce_kernel<<<1, 256, 0, st>>>(cpart, grid, 32, 3 * L.basis, grad_params + L.off_coef, 3 * L.basis, nullptr);
+      angio::note_launch(); small_reduce_kernel<<<3 * L.basis, 128, 0, st>>>(cpart, grid, 32, 3 * L.basis, grad_params + L.off_coef, 3 * L.basis, nullptr);
     }
   }
   // (3) weight gradients
@@ -1004,7 +1003,7 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
     const uint8_t* a_last = sv + n_tiles * kA0Bytes + (int64_t)L.n_hidden * n_tiles * kActBytes;
     angio::note_launch(); outgrad_partial_kernel<<<kOutgradBlocks, 256, 0, st>>>(a_last, grad_out, n, in.n_dev, opart);
     const int lo = L.n_linear - 1;
-    angio::note_launch(); small_reduce_kernel<<<1, 256, 0, st>>>(opart, kOutgradBlocks, 132, 129, grad_params + L.off_w[lo], 128, grad_params + L.off_b[lo]);
+    angio::note_launch(); small_reduce_kernel<<<129, 128, 0, st>>>(opart, kOutgradBlocks, 132, 129, grad_params + L.off_w[lo], 128, grad_params + L.off_b[lo]);
   }
   return finish_launch("tc_backward");
 }
