@@ -218,6 +218,44 @@ class Trainer:
             g.occs.copy_(occs); g._binary.copy_(binary); g.occs_mean_host = mean
         self.ray_gen.set_state(snap["gens"][0]); self.grid_gen.set_state(snap["gens"][1])
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save_checkpoint(self, filename, extra=None):
+        """One .pth in the reference's checkpoint layout (CPPN.save, /root/reference/model/CPPN.py:261-276: version /
+        parameters / training_information / model state_dict) whose `training_information` additionally carries what a true
+        resume needs and the reference never stored: Adam moments, step counters, lr, both occupancy grids, RNG states.
+        A checkpoint written here loads in the reference (it only reads 'parameters' and 'model'), and vice versa."""
+        grids = [g for g in (self.acc_grid, self.vessel_acc_grid) if g is not None]
+        info = dict(extra or {})
+        info["resume"] = dict(
+            n_iter=self.n_iter, n_iter_adam=self.n_iter_adam, lr=self.lr,
+            exp_avg=self.exp_avg.detach().cpu(), exp_avg_sq=self.exp_avg_sq.detach().cpu(),
+            grids=[dict(occs=g.occs.detach().cpu(), binary=g._binary.detach().cpu(), occs_mean=g.occs_mean_host) for g in grids],
+            ray_gen=self.ray_gen.get_state().cpu(), grid_gen=self.grid_gen.get_state().cpu(),
+            sampler_seed_stream=(self.pool._seed_streams[id(self.ray_gen)].bit_generator.state
+                                 if id(self.ray_gen) in self.pool._seed_streams else None))
+        self.model.save(filename, info)
+
+    def load_checkpoint(self, filename):
+        """Restore model + optimiser + grids + counters from save_checkpoint (or just the model from a reference .pth)."""
+        ck = torch.load(filename, map_location="cpu", weights_only=False)
+        self.model.load_state_dict(ck["model"])
+        if self.flat.data_ptr() != self.model._flat.data_ptr():
+            raise RuntimeError("load_state_dict re-allocated the flat parameter buffer")
+        res = (ck.get("training_information") or {}).get("resume")
+        if res is None:
+            return ck
+        self.n_iter, self.n_iter_adam, self.lr = res["n_iter"], res["n_iter_adam"], res["lr"]
+        self.exp_avg.copy_(res["exp_avg"]); self.exp_avg_sq.copy_(res["exp_avg_sq"])
+        grids = [g for g in (self.acc_grid, self.vessel_acc_grid) if g is not None]
+        for g, st in zip(grids, res["grids"]):
+            g.occs.copy_(st["occs"]); g._binary.copy_(st["binary"]); g.occs_mean_host = st["occs_mean"]
+        self.ray_gen.set_state(res["ray_gen"]); self.grid_gen.set_state(res["grid_gen"])
+        if res.get("sampler_seed_stream") is not None:               # host-side seed stream of the on-device ray sampler
+            rng = np.random.default_rng(0)
+            rng.bit_generator.state = res["sampler_seed_stream"]
+            self.pool._seed_streams[id(self.ray_gen)] = rng
+        return ck
+
     # ------------------------------------------------------------------ evaluation (run_nerf_acc.py:338-357)
     @torch.no_grad()
     def render_view(self, v, binary_thresh=None):

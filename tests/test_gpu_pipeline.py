@@ -263,6 +263,38 @@ def test_sync_free_step_equals_one_sync_step(A):
     assert out["n_samples"] == 0 and tr.flat.equal(before) and bool((out["pix"] == 1).all())
 
 
+def test_checkpoint_resume_is_exact(A, tmp_path):
+    """save_checkpoint -> fresh Trainer.load_checkpoint -> the continued run is bit-identical to the uninterrupted one; the
+    file has the reference's .pth layout (model/CPPN.py:261-276) and its state_dict loads into a new CPPN."""
+    import bench
+    from nerf_for_angiography_b200.data import make_dataset
+    from nerf_for_angiography_b200.train import Trainer
+    dev = torch.device("cuda", 0)
+    w = dict(bench.WORKLOADS["tiny"], rays=1024)
+    pool, info = make_dataset(img_size=32, thetas=w["thetas"], kind="ct", volume_res=32, device=dev)
+
+    def make():
+        torch.manual_seed(0)
+        return Trainer(A.CPPN(bench.model_def(w, dev, "bf16")).to(dev), pool, info["near"], info["far"], n_rays=w["rays"], seed=0)
+    tr = make()
+    for _ in range(18):                                                # crosses a grid refresh (iteration 16)
+        tr.step()
+    path = str(tmp_path / "ck.pth")
+    tr.save_checkpoint(path, extra={"note": "unit test"})
+    ref_losses = [float(tr.step()["loss"]) for _ in range(3)]
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(ck) == {"version", "parameters", "training_information", "model"} and ck["training_information"]["note"] == "unit test"
+    assert {"early_pts_layers.0.weight", "output_linear.0.bias", "fourier_coefficients", "img1", "img2"} <= set(ck["model"])
+    tr2 = make()
+    pool._seed_streams = {}
+    tr2.load_checkpoint(path)
+    got = [float(tr2.step()["loss"]) for _ in range(3)]
+    assert np.allclose(got, ref_losses, rtol=1e-6, atol=0)           # the scalar loss is summed with float atomics
+    assert tr2.acc_grid.occs.equal(tr.acc_grid.occs) and tr2.n_iter == tr.n_iter
+    assert tr2.flat.equal(tr.flat)                                     # same rays, same kernels, fixed-order reductions
+    m = A.CPPN(ck["parameters"]); m.load_state_dict(ck["model"])      # what the reference does with a checkpoint
+
+
 # ------------------------------------------------------------------------------------------------ bf16 tcgen05 backward
 @pytest.mark.parametrize("pos_enc,L,n", [("fourier", 4, 128 * 148 * 2 + 300), ("none", 4, 5000), ("fourier", 2, 777), ("fourier", 4, 100)])
 def test_mlp_bf16_tensor_core_backward(A, pos_enc, L, n):

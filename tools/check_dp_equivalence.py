@@ -1,0 +1,61 @@
+"""Data-parallel determinism check: an N-rank step on the batches B_0 .. B_{N-1} must produce the gradient and
+parameters of a 1-rank step on the concatenated batch, to fp32 re-association tolerance.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/check_dp_equivalence.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import nerf_for_angiography_b200 as A  # noqa: E402
+from nerf_for_angiography_b200.data import make_dataset  # noqa: E402
+from nerf_for_angiography_b200.train import Trainer  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    w = dict(bench.WORKLOADS["tiny"], rays=4096)
+    R = w["rays"]
+    torch.manual_seed(0)
+    pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], kind="ct", volume_res=w["vol"], device=dev)
+    gen = torch.Generator(device=dev).manual_seed(123)
+    o, d, t = pool.sample(R * world, generator=gen)                  # the same global batch on every rank
+
+    def fresh():
+        torch.manual_seed(0)
+        return A.CPPN(bench.model_def(w, dev, "bf16")).to(dev)
+
+    # 1-rank reference on the concatenated batch (before the process group exists => world = 1)
+    ref = Trainer(fresh(), pool, info["near"], info["far"], n_rays=R * world, seed=0)
+    ref.step(rays=(o, d, t))
+    g_ref, p_ref = ref.grad[:-1].clone(), ref.flat.clone()
+
+    torch.distributed.init_process_group("nccl", device_id=dev)
+    tr = Trainer(fresh(), pool, info["near"], info["far"], n_rays=R, seed=0)
+    assert tr.world == world
+    sl = slice(rank * R, (rank + 1) * R)
+    out = tr.step(rays=(o[sl].contiguous(), d[sl].contiguous(), t[sl].contiguous()))
+    g, p = tr.grad[:-1], tr.flat
+    scale = float(g_ref.abs().max())
+    eg = float((g - g_ref).abs().max()) / scale
+    ep = float((p - p_ref).abs().max())
+    kept = torch.tensor([float(out["n_samples"])], device=dev)
+    torch.distributed.all_reduce(kept)
+    if rank == 0:
+        print(f"world={world} rays/rank={R}: max |grad - grad_1rank| / max|grad| = {eg:.2e}, max |param - param_1rank| = {ep:.2e}, "
+              f"kept samples {int(kept.item())} vs {ref.last['n_samples']} (1 rank)")
+        assert int(kept.item()) == ref.last["n_samples"]
+        assert eg <= 1e-5 and ep <= 2.1e-4, (eg, ep)
+        print("DP EQUIVALENCE OK")
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
