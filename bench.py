@@ -177,6 +177,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not sample clocks during the timed region")
+    ap.add_argument("--full-visibility", action="store_true",
+                    help="evaluate the visibility-pass MLP on EVERY marched sample (the reference's order of operations) instead of the "
+                         "two-phase pass with early ray termination; the kept samples are bit-identical either way")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +204,7 @@ def main():
     pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], test_view=(135.0, 135.0), kind="ct", volume_res=w["vol"],
                               device=dev, seed=0)
     model = A.CPPN(model_def(w, dev, args.precision)).to(dev)          # same seed => identical weights on every rank
-    tr = Trainer(model, pool, info["near"], info["far"], n_rays=w["rays"], seed=0)
+    tr = Trainer(model, pool, info["near"], info["far"], n_rays=w["rays"], seed=0, early_termination=0 if args.full_visibility else 32)
     R = w["rays"]
 
     def sync_all():
@@ -227,7 +230,7 @@ def main():
     if not args.no_clocks:
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tr.kernel_events, tr.kernel_totals = [], []                        # event pairs around the visibility-pass MLP launch
+    tr.kernel_events = []                                              # (start, end, sample count) per visibility-pass MLP launch
     step_totals = []                                                   # device counters of every step, read after the timed region
     torch.cuda.profiler.start()                                        # ncu --profile-from-start off captures exactly the timed region
     e0.record()
@@ -245,8 +248,8 @@ def main():
         raise RuntimeError("ray sampler overflow during the timed region")
     n_pre_total = sum(t[0] for t in host_totals)
     n_kept_total = sum(t[1] for t in host_totals)
-    kernel_ms = [a.elapsed_time(b) for a, b in tr.kernel_events]
-    kernel_n = [(t.tolist() if isinstance(t, torch.Tensor) else list(t))[0] for t in tr.kernel_totals]
+    kernel_ms = [a.elapsed_time(b) for a, b, _ in tr.kernel_events]
+    kernel_n = [int(c.item()) if isinstance(c, torch.Tensor) else int(c) for _, _, c in tr.kernel_events]   # samples each launch evaluated
     tr.kernel_events = None
     last_loss = float(out["loss"])
 
@@ -281,12 +284,18 @@ def main():
         flop = MLP_FWD_FLOP.get((w["enc"], w["L"], w["H"]))
         roofline = None
         if kernel_ms and flop and args.precision == "bf16":
-            # the first timed step may include a grid refresh; every entry is one launch of the visibility-pass MLP
-            ach = float(np.mean([flop * n / (t * 1e-3) for n, t in zip(kernel_n, kernel_ms) if t > 0])) * 1e-12
-            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-            roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                        "kernel": "mlp_fwd_tc_kernel<ALPHA> (no-grad visibility pass)", "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained"
-                        if peaks else "fallback", "avg_launch_ms": float(np.mean(kernel_ms)), "samples_per_launch": float(np.mean(kernel_n))}
+            # every entry is one launch of the visibility-pass MLP forward (two per step with early ray termination: the first
+            # 32 samples of every ray, then the rest of the rays still alive -- usually none at random init).  Launches that
+            # do not fill the 148 SMs twice are left out; the rest are weighted by the samples they evaluated.
+            big = [(n, t) for n, t in zip(kernel_n, kernel_ms) if t > 0 and n >= 2 * 128 * 148]
+            if big:
+                ach = flop * sum(n for n, _ in big) / (sum(t for _, t in big) * 1e-3) * 1e-12
+                peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+                roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                            "kernel": "mlp_fwd_tc_kernel<ALPHA> (no-grad visibility pass)",
+                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
+                            "avg_launch_ms": float(np.mean([t for _, t in big])), "samples_per_launch": float(np.mean([n for n, _ in big])),
+                            "launches_timed": len(big)}
         cpu = None
         if not args.no_cpu_baseline:
             n_cpu = 1024 if args.workload != "tiny" else 256
@@ -300,7 +309,10 @@ def main():
                 "config": {"workload": args.workload, "detector": f"{w['img']}x{w['img']}", "views": len(w["thetas"]) + 1,
                            "mlp": f"{w['L']}x{w['H']} {w['enc']}", "rays_per_gpu_per_step": R, "march_steps": 300, "grid": "128^3",
                            "l2": "no flush: every step draws fresh rays and streams ~15 M marched samples (>= 250 MB of sample "
-                                 "arrays), larger than the 126 MB L2"},
+                                 "arrays), larger than the 126 MB L2",
+                           "visibility_pass": "every marched sample (reference order)" if args.full_visibility else
+                                              "two-phase with early ray termination (kept samples bit-identical to evaluating every sample)"},
+                "mlp_evals_visibility_per_step": float(sum(kernel_n)) / max(args.steps, 1),
                 "samples_per_s_marched": float(cnt[0]) / (ms * 1e-3), "samples_per_s_kept": float(cnt[1]) / (ms * 1e-3),
                 "clocks": clk, "gpu_launches": launches,
                 "e2e": {"value": rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": R * 28, "d2h_bytes_per_step": 4 + 8},

@@ -111,6 +111,21 @@ ANGIO_API int angio_grid_query(const float* points, int64_t n, const float* roi_
 ANGIO_API int angio_visibility_mask(const float* alphas, const int32_t* offsets, int64_t n_rays,
                           float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts,
                           void* stream);
+/* Two-phase visibility pass (early ray termination; the kept set is bit-identical to evaluating every sample): phase A
+ * evaluates the first k0 samples of every ray, angio_visibility_head marks the rays whose transmittance after them is still
+ * >= early_stop_eps, phase B evaluates the remaining samples of those rays only.  The sample subsets are handed to
+ * angio_mlp_forward as index lists (angio_samples.sample_idx):
+ *   counts[r]      = number of samples of ray r with local index in [skip, skip + limit)   (limit < 0: unbounded;
+ *                    0 where alive[r] == 0, alive may be NULL)
+ *   sample_ids[..] = their global indices, rays in order, after an exclusive scan of counts (seg_offsets)
+ * angio_visibility_mask stops reading alphas behind the termination point (alphas must lie in [0, 1]).
+ */
+ANGIO_API int angio_ray_segment_counts(const int32_t* offsets, int64_t n_rays, int32_t skip, int32_t limit,
+                             const uint8_t* alive, int32_t* counts, void* stream);
+ANGIO_API int angio_ray_segment_ids(const int32_t* offsets, const int32_t* seg_offsets, int64_t n_rays, int32_t skip,
+                          int32_t* sample_ids, void* stream);
+ANGIO_API int angio_visibility_head(const float* alphas, const int32_t* offsets, int64_t n_rays, int32_t k0,
+                          float early_stop_eps, uint8_t* alive, void* stream);
 ANGIO_API int angio_compact_samples(const uint8_t* keep, const int32_t* offsets, const int32_t* new_offsets,
                           int64_t n_rays, const float* t_starts, const float* t_ends,
                           int32_t* ray_idx_out, float* t_starts_out, float* t_ends_out, void* stream);
@@ -141,6 +156,9 @@ typedef struct angio_samples {
   const int32_t* ray_idx; /* [n] */
   const float* t_starts;  /* [n] */
   const float* t_ends;    /* [n] */
+  const int32_t* sample_idx; /* optional [n] index list: sample k of this call is element sample_idx[k] of ray_idx /
+                                t_starts / t_ends, and its output goes to out[sample_idx[k]] (inference forward of the
+                                bf16 path only; NULL = identity) */
   const int32_t* n_dev;   /* optional DEVICE-resident sample count: kernels process min(*n_dev, n) samples, so a marcher
                              that leaves its total on the device can feed the MLP without a host sync (n = capacity of
                              the arrays; tile-image layouts of the saved activations are strided by that capacity).

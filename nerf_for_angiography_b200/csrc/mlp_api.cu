@@ -84,6 +84,10 @@ extern "C" int angio_mlp_forward(const angio_mlp_desc* desc, const float* params
     angio::set_error("angio_mlp_forward: a device-resident sample count (n_dev) is only supported by the bf16 path");
     return ANGIO_ERR_UNSUPPORTED;
   }
+  if (in->sample_idx && (precision != ANGIO_PREC_BF16 || saved || in->points)) {
+    angio::set_error("angio_mlp_forward: sample_idx is only supported by the bf16 inference forward on ray samples");
+    return ANGIO_ERR_UNSUPPORTED;
+  }
   if (precision == ANGIO_PREC_FP32)
     return angio::simt_forward(L, params, *in, out_mode, out, saved, workspace, workspace_bytes, angio::as_stream(stream));
   if (precision == ANGIO_PREC_BF16) {
@@ -104,6 +108,7 @@ extern "C" int angio_mlp_backward(const angio_mlp_desc* desc, const float* param
   if (int rc = check_samples(in, "angio_mlp_backward")) return rc;
   ANGIO_REQUIRE(in->n == 0 || (saved && grad_out), "angio_mlp_backward: needs saved activations and grad_out");
   ANGIO_REQUIRE(!in->n_dev || precision == ANGIO_PREC_BF16, "angio_mlp_backward: n_dev is only supported by the bf16 path");
+  ANGIO_REQUIRE(!in->sample_idx, "angio_mlp_backward: sample_idx is not supported");
   if (precision == ANGIO_PREC_FP32)
     return angio::simt_backward(L, params, *in, saved, grad_out, grad_params, workspace, workspace_bytes, angio::as_stream(stream));
   if (precision == ANGIO_PREC_BF16) {

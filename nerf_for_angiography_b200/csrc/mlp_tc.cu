@@ -377,15 +377,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     // Software pipeline over this group's tiles: the inputs of tile j+2 (two dependent global loads: ray id -> origin /
     // direction) are fetched while tile j runs its layers, and tile j+2 is encoded and handed to the tensor core BEFORE
     // tile j's output is exchanged and stored, so the slot's pipeline never waits on global memory between tiles.
-    auto fetch = [&](int64_t jt, float (&xx)[3], float& dtt, bool& vv) {
-      const int64_t ii = (blockIdx.x + jt * gridDim.x) * kTile + row;
+    auto fetch = [&](int64_t jt, float (&xx)[3], float& dtt, bool& vv, int64_t& idx) {
+      int64_t ii = (blockIdx.x + jt * gridDim.x) * kTile + row;
       vv = (jt < my_tiles) && (ii < n);
       xx[0] = xx[1] = xx[2] = 0.f;
       dtt = 0.f;
       if (vv) {
+        if (in.sample_idx) ii = in.sample_idx[ii];      // index list: a subset of the sample arrays (two-phase visibility pass)
         angio::sample_position(in, ii, xx);
         if (OUT_MODE == ANGIO_OUT_ALPHA) dtt = in.t_ends[ii] - in.t_starts[ii];
       }
+      idx = ii;
     };
     // features of tile jt: the two halves split the 8-column chunks of a_0 (chunk c8 belongs to half c8 & 1)
     // The features live in their own TMEM region (a0), so the NEXT tile is encoded while the tensor core runs the current
@@ -411,14 +413,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     };
     float xn[3], dtn;
     bool vn;
-    fetch(g, xn, dtn, vn);
+    int64_t in_;
+    fetch(g, xn, dtn, vn, in_);
     if (g < my_tiles) { encode(g, xn); signal_a_ready(&bars.a_ready[g], lane); }
     for (int64_t j = g; j < my_tiles; j += 2) {
       const int64_t tile = blockIdx.x + j * gridDim.x;
-      const int64_t i = tile * kTile + row;
+      const int64_t i = in_;                      // where this row's output goes
       const bool valid = vn;
       const float dt = dtn;
-      fetch(j + 2, xn, dtn, vn);                  // in flight during this tile's layers
+      fetch(j + 2, xn, dtn, vn, in_);             // in flight during this tile's layers
       // ---- hidden layers: acc + bias -> relu -> bf16 -> next A operand (this warp: columns [64h, 64h+64))
       for (int l = 0; l < P.n_hidden; ++l) {
         mbar_wait(&bars.acc_ready[g], phase);

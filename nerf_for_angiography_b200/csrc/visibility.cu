@@ -38,6 +38,13 @@ __global__ void __launch_bounds__(256) visibility_mask_kernel(const float* __res
       if (thre > 0.0f) vis = vis && (a >= thre);
       if (valid) keep[i] = vis ? 1 : 0;
       kept += __popc(__ballot_sync(0xffffffffu, vis));
+      if (T < eps) {
+        // early ray termination: alpha in [0, 1] makes T non-increasing, so nothing behind this chunk can be visible;
+        // the rest of the ray is marked invisible WITHOUT reading its alphas (the two-phase visibility pass never
+        // computes them)
+        for (int k = base + 32 + lane; k < end; k += 32) keep[k] = 0;
+        break;
+      }
     }
     if (lane == 0) kept_counts[r] = kept;
   }
@@ -67,9 +74,53 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict_
         t1_out[pos] = t_ends[i];
       }
       dst += __popc(m);
+      if (dst == dst_end) break;   // every kept sample of this ray has been written
     }
   }
 }
+
+// ---- two-phase visibility pass (early ray termination).  The reference evaluates alpha_fn on EVERY marched sample and
+// filters afterwards (nerf_helpers_acc.py:11-29); a sample behind the point where the transmittance fell below
+// early_stop_eps can never be kept, whatever its alpha.  Phase A evaluates the first k0 samples of every ray, phase B the
+// remaining samples of the rays that are still alive after them; the kept set is bit-identical to the full evaluation.
+
+// counts[r] = number of samples of ray r in [skip, skip + limit) (limit < 0: no limit); 0 for rays with alive[r] == 0
+__global__ void __launch_bounds__(256) segment_counts_kernel(const int32_t* __restrict__ offsets, int64_t n_rays, int skip, int limit,
+                                                             const uint8_t* __restrict__ alive, int32_t* __restrict__ counts) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  int c = offsets[r + 1] - offsets[r] - skip;
+  if (c < 0) c = 0;
+  if (limit >= 0 && c > limit) c = limit;
+  if (alive && !alive[r]) c = 0;
+  counts[r] = c;
+}
+
+// sample_ids[seg_offsets[r] + j] = offsets[r] + skip + j   for j < seg_offsets[r+1] - seg_offsets[r]   (warp per ray)
+__global__ void __launch_bounds__(256) segment_ids_kernel(const int32_t* __restrict__ offsets, const int32_t* __restrict__ seg_offsets,
+                                                          int64_t n_rays, int skip, int32_t* __restrict__ sample_ids) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  for (int64_t r = warp_global; r < n_rays; r += n_warps) {
+    const int dst = seg_offsets[r], m = seg_offsets[r + 1] - dst, src = offsets[r] + skip;
+    for (int j = lane; j < m; j += 32) sample_ids[dst + j] = src + j;
+  }
+}
+
+// alive[r] = ray r has more than k0 samples and its transmittance after the first k0 is still >= eps (thread per ray; the
+// product is accumulated in sample order exactly like visibility_mask_kernel)
+__global__ void __launch_bounds__(256) visibility_head_kernel(const float* __restrict__ alphas, const int32_t* __restrict__ offsets,
+                                                              int64_t n_rays, int k0, float eps, uint8_t* __restrict__ alive) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  const int beg = offsets[r], cnt = offsets[r + 1] - beg;
+  if (cnt <= k0) { alive[r] = 0; return; }
+  float T = 1.0f;
+  for (int j = 0; j < k0; ++j) T = __fmul_rn(T, __fsub_rn(1.0f, alphas[beg + j]));
+  alive[r] = (T >= eps) ? 1 : 0;
+}
+
 
 int warp_grid(int64_t n_rays) {
   int64_t blocks = (n_rays + 7) / 8;  // 8 warps per 256-thread block, one ray per warp per pass
@@ -87,6 +138,30 @@ extern "C" int angio_visibility_mask(const float* alphas, const int32_t* offsets
   angio::note_launch(); visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
                                                                                  alpha_thre, keep, kept_counts);
   return angio::finish_launch("angio_visibility_mask");
+}
+
+extern "C" int angio_ray_segment_counts(const int32_t* offsets, int64_t n_rays, int32_t skip, int32_t limit, const uint8_t* alive,
+                                       int32_t* counts, void* stream) {
+  ANGIO_REQUIRE(offsets && counts && n_rays >= 0 && skip >= 0, "angio_ray_segment_counts: bad arguments");
+  if (n_rays == 0) return 0;
+  angio::note_launch(); segment_counts_kernel<<<angio::blocks_for(n_rays, 256), 256, 0, angio::as_stream(stream)>>>(offsets, n_rays, skip, limit, alive, counts);
+  return angio::finish_launch("angio_ray_segment_counts");
+}
+
+extern "C" int angio_ray_segment_ids(const int32_t* offsets, const int32_t* seg_offsets, int64_t n_rays, int32_t skip, int32_t* sample_ids,
+                                     void* stream) {
+  ANGIO_REQUIRE(offsets && seg_offsets && sample_ids && n_rays >= 0 && skip >= 0, "angio_ray_segment_ids: bad arguments");
+  if (n_rays == 0) return 0;
+  angio::note_launch(); segment_ids_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(offsets, seg_offsets, n_rays, skip, sample_ids);
+  return angio::finish_launch("angio_ray_segment_ids");
+}
+
+extern "C" int angio_visibility_head(const float* alphas, const int32_t* offsets, int64_t n_rays, int32_t k0, float early_stop_eps,
+                                     uint8_t* alive, void* stream) {
+  ANGIO_REQUIRE(alphas && offsets && alive && n_rays >= 0 && k0 > 0, "angio_visibility_head: bad arguments");
+  if (n_rays == 0) return 0;
+  angio::note_launch(); visibility_head_kernel<<<angio::blocks_for(n_rays, 256), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, k0, early_stop_eps, alive);
+  return angio::finish_launch("angio_visibility_head");
 }
 
 extern "C" int angio_compact_samples(const uint8_t* keep, const int32_t* offsets, const int32_t* new_offsets, int64_t n_rays,

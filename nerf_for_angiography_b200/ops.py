@@ -230,6 +230,41 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     return ray_idx, t0, t1, new_offsets, (keep if host_totals is None else host_totals)
 
 
+def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t_starts, t_ends, offsets, early_stop_eps, k0=32, timing=None):
+    """alpha_fn over the marched samples with early ray termination (see angio_b200.h "Two-phase visibility pass"):
+    phase A = the first k0 samples of every ray, phase B = the rest of the rays whose transmittance is still >= early_stop_eps
+    after them.  Entries of the returned alphas behind a ray's termination point are undefined; visibility_compact never
+    reads them.  No host sync: the list lengths stay on the device.  Returns (alphas, evaluated int32[2] device tensor)."""
+    lib = _lib.load()
+    if k0 % 32 != 0 or k0 <= 0:
+        raise ValueError("k0 must be a positive multiple of 32 (the visibility kernel's chunk)")
+    offsets = _chk(offsets, torch.int32, "offsets", 1)
+    R, dev = offsets.numel() - 1, offsets.device
+    cap = t_starts.numel()
+    alphas = torch.empty((cap,), dtype=torch.float32, device=dev)
+    evaluated = torch.zeros((2,), dtype=torch.int32, device=dev)
+    counts = torch.empty((R,), dtype=torch.int32, device=dev)
+    alive = torch.empty((R,), dtype=torch.uint8, device=dev)
+    kw = dict(rays_o=rays_o, rays_d=rays_d, ray_idx=ray_idx, t_starts=t_starts, t_ends=t_ends)
+    for phase, (skip, limit, mask, size) in enumerate(((0, k0, None, min(cap, R * k0)), (k0, -1, alive, cap))):
+        _lib.check(lib.angio_ray_segment_counts(_p(offsets), R, skip, limit, _p(mask), _p(counts), _stream()), "angio_ray_segment_counts")
+        seg = exclusive_scan(counts, evaluated[phase:phase + 1])
+        ids = torch.empty((size,), dtype=torch.int32, device=dev)
+        if size > 0:
+            _lib.check(lib.angio_ray_segment_ids(_p(offsets), _p(seg), R, skip, _p(ids), _stream()), "angio_ray_segment_ids")
+            if timing is not None:                         # bench.py: CUDA events around each MLP launch + its device sample count
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            mlp_forward(desc, params, packed, OUT_ALPHA, precision, out=alphas, sample_idx=ids, n_dev=seg[R:R + 1], **kw)
+            if timing is not None:
+                ev1.record()
+                timing.append((ev0, ev1, evaluated[phase:phase + 1]))
+        if phase == 0:
+            _lib.check(lib.angio_visibility_head(_p(alphas), _p(offsets), R, int(k0), float(early_stop_eps), _p(alive), _stream()),
+                       "angio_visibility_head")
+    return alphas, evaluated
+
+
 # ------------------------------------------------------------------------------------------------ composite
 def composite_forward(logits, t_starts, t_ends, offsets, zero_mask=None):
     lib = _lib.load()
@@ -297,7 +332,7 @@ def mlp_pack(desc, params, packed=None):
     return packed
 
 
-def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None, t_ends=None, n_dev=None):
+def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None, t_ends=None, n_dev=None, sample_idx=None):
     if points is not None:
         points = _chk(points, torch.float32, "points", 2)
         if points.shape[1] != 3:
@@ -311,7 +346,10 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
     t_starts = _chk(t_starts, torch.float32, "t_starts", 1, allow_none=points is not None)
     t_ends = _chk(t_ends, torch.float32, "t_ends", 1, allow_none=points is not None)
     n_dev = _chk(n_dev, torch.int32, "n_dev", allow_none=True)
-    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(n_dev))
+    sample_idx = _chk(sample_idx, torch.int32, "sample_idx", 1, allow_none=True)
+    if sample_idx is not None:
+        n = sample_idx.numel()
+    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(sample_idx), _p(n_dev))
     return s, n
 
 
@@ -345,13 +383,19 @@ class BufferPool:
         return self.get(key, n * item, device)[:n * item].view(dtype)
 
 
-def mlp_forward(desc, params, packed, out_mode, precision, saved=False, pool=None, **sample_kw):
-    """Returns out[n] (and the saved-activation buffer when saved=True)."""
+def mlp_forward(desc, params, packed, out_mode, precision, saved=False, pool=None, out=None, **sample_kw):
+    """Returns out[n] (and the saved-activation buffer when saved=True).  With sample_idx (an int32 index list into the
+    ray-sample arrays) only those samples are evaluated and their results land at out[sample_idx[k]]; pass `out`
+    (sized like t_starts) to collect several such calls in one array."""
     lib = _lib.load()
     params = _chk(params, torch.float32, "params", 1)
     s, n = _samples(**sample_kw)
     dev = params.device
-    out = torch.empty((n,), dtype=torch.float32, device=dev)
+    if out is None:
+        n_out = sample_kw["t_starts"].numel() if sample_kw.get("sample_idx") is not None else n
+        out = torch.empty((n_out,), dtype=torch.float32, device=dev)
+    else:
+        out = _chk(out, torch.float32, "out", 1)
     saved_buf = None
     if saved:
         sb = int(lib.angio_mlp_saved_bytes(ctypes.byref(desc), n, precision))

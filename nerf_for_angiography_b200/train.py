@@ -40,7 +40,7 @@ class StepResult(dict):
 class Trainer:
     def __init__(self, model: CPPN, pool, near, far, n_rays=5625, n_steps=300, half_extent=100.0, grid_resolution=128,
                  lr=1e-4, decay_rate=0.1, decay_steps=500000, early_stop_eps=1e-2, alpha_thre=1e-4, vessel_alpha_thre=5e-2,
-                 vessel_grid=True, seed=0, process_group=None, sync_free="auto", memory_fraction=0.6):
+                 vessel_grid=True, seed=0, process_group=None, sync_free="auto", memory_fraction=0.6, early_termination=32):
         self.model = model
         self.pool = pool
         self.dev = pool.device
@@ -74,9 +74,11 @@ class Trainer:
         self.ray_gen = torch.Generator(device=self.dev).manual_seed(seed + 1000 * self.rank + 1)
         self.grid_gen = torch.Generator(device=self.dev).manual_seed(seed)
         self.last = {}
-        self.kernel_events = None     # bench.py: list of (start, end) CUDA events around the visibility-pass MLP launch
-        self.kernel_totals = []       # ... and the step's device counters (sample count of that launch = totals[0])
+        self.kernel_events = None     # bench.py: list of (start event, end event, sample count) per visibility-pass MLP launch
         self.sync_free = self._plan_memory(sync_free, memory_fraction)
+        # visibility pass with early ray termination (bf16 path): number of leading samples per ray evaluated before the rays
+        # that are already opaque are dropped (multiple of 32); 0 / None = evaluate every marched sample like the reference
+        self.early_termination = int(early_termination) if early_termination else 0
 
     # ------------------------------------------------------------------ memory plan
     def _plan_memory(self, mode, fraction):
@@ -129,16 +131,20 @@ class Trainer:
                                              self.step_size, capacity=cap, total_out=totals[0:1] if bf16 else None)
         n_pre = ray_idx.numel()
         if n_pre > 0:
-            if self.kernel_events is not None:
-                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
-                                     rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1,
-                                     n_dev=offsets[R:R + 1] if bf16 else None)
-            if self.kernel_events is not None:
-                ev1.record()
-                self.kernel_events.append((ev0, ev1))
-                self.kernel_totals.append(totals if bf16 else [n_pre])
+            if bf16 and self.early_termination:
+                # same kept set as evaluating every sample; only samples that can still be visible reach the MLP
+                alphas, _ = ops.alphas_two_phase(self.model._desc, self.flat, self.packed, self.model._precision_id, o, d, ray_idx,
+                                                 t0, t1, offsets, self.early_stop_eps, k0=self.early_termination, timing=self.kernel_events)
+            else:
+                if self.kernel_events is not None:
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
+                                         rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1,
+                                         n_dev=offsets[R:R + 1] if bf16 else None)
+                if self.kernel_events is not None:
+                    ev1.record()
+                    self.kernel_events.append((ev0, ev1, totals[0:1] if bf16 else n_pre))
             thre = min(self.alpha_thre, g.occs_mean_host)
             ray_idx, t0, t1, offsets, host_totals = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre,
                                                                           totals=totals if bf16 else None,

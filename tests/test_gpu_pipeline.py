@@ -263,6 +263,37 @@ def test_sync_free_step_equals_one_sync_step(A):
     assert out["n_samples"] == 0 and tr.flat.equal(before) and bool((out["pix"] == 1).all())
 
 
+@pytest.mark.parametrize("bias_shift", [0.0, -3.0, -9.0])
+def test_two_phase_visibility_equals_full_evaluation(A, bias_shift):
+    """Early ray termination: alphas only for the first 32 samples of each ray + the rest of the rays still alive, against
+    alphas for every sample -- same keep mask, same compacted samples, bit for bit (dense field: all rays die early;
+    thin field: all survive; in between: mixed)."""
+    og, gg, roi, o, d = _small_scene(A, res=32, W=40)
+    p = ocppn.init_params(4, 128, "fourier", 5, 0.05, seed=7)
+    p["output_linear.0.bias"] = p["output_linear.0.bias"] + bias_shift
+    model = A.CPPN(_model_def(4, 128, "fourier", "bf16"))
+    model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda"); model._ensure_flat()
+    packed = A.ops.mlp_pack(model._desc, model._flat)
+    ro, rd = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    aabb = np.array(roi, np.float32)
+    step = 200.0 / 300
+    ri, t0, t1, off = A.ops.march(ro, rd, aabb, aabb, 32, gg._binary_u8(), 1400.0, 1600.0, step)
+    kw = dict(rays_o=ro, rays_d=rd, ray_idx=ri, t_starts=t0, t_ends=t1)
+    full = A.ops.mlp_forward(model._desc, model._flat, packed, A.ops.OUT_ALPHA, A.ops.PREC_BF16, **kw)
+    two, evaluated = A.ops.alphas_two_phase(model._desc, model._flat, packed, A.ops.PREC_BF16, ro, rd, ri, t0, t1, off, 1e-2, k0=32)
+    ev = evaluated.tolist()
+    assert ev[0] == int(torch.clamp(off[1:] - off[:-1], max=32).sum()) and ev[0] + ev[1] <= ri.numel()
+    a = A.ops.visibility_compact(full, off, t0, t1, 1e-2, 1e-4)
+    b = A.ops.visibility_compact(two, off, t0, t1, 1e-2, 1e-4)
+    for x, y in zip(a, b):
+        assert x.equal(y)
+    if bias_shift == 0.0:
+        assert ev[1] < 0.5 * (ri.numel() - ev[0])             # dense field: most rays are opaque after 32 samples
+    if bias_shift == -9.0:
+        assert ev[0] + ev[1] == ri.numel()                    # thin field: nothing terminates, every sample is evaluated
+
+
 def test_checkpoint_resume_is_exact(A, tmp_path):
     """save_checkpoint -> fresh Trainer.load_checkpoint -> the continued run is bit-identical to the uninterrupted one; the
     file has the reference's .pth layout (model/CPPN.py:261-276) and its state_dict loads into a new CPPN."""
