@@ -85,19 +85,23 @@ ANGIO_API int angio_raygen_flat(const double* cam2world, const int64_t* ids, int
  * _C.ray_marching (called at nerf/nerf_helpers_acc.py:29).  binary: [res,res,res] uint8 (torch.bool),
  * x-major.  roi / aabb: 6 floats (min xyz, max xyz) on the HOST.
  */
-/* pass 0+1: t_min/t_max per ray (slab test clamped to [near,far]) and per-ray sample counts */
+/* pass 0+1: t_min/t_max per ray (slab test clamped to [near,far]) and per-ray sample counts.
+ * runs (optional, angio_march_runs_bytes(n_rays) bytes): the count pass records each ray's runs of consecutive samples
+ * (start t0 + length, up to 8 per ray); given the same table, the write pass replays the fp32 t-chain of the runs instead of
+ * marching the grid a second time (rays with more runs are re-marched).  The samples are bit-identical either way. */
+ANGIO_API int64_t angio_march_runs_bytes(int64_t n_rays);
 ANGIO_API int angio_march_count(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host,
                       const float* roi_host, int32_t res, const uint8_t* binary, float near_plane,
                       float far_plane, float step_size, float* t_min, float* t_max, int32_t* counts,
-                      void* stream);
+                      void* runs, void* stream);
 /* exclusive scan: offsets[n+1] int32 (offsets[n] = total); also copies the total to *total_out if not NULL */
 ANGIO_API int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out,
                              void* stream);
 /* pass 2: write samples.  ray_idx [n] int32, t_starts / t_ends [n] float32 */
 ANGIO_API int angio_march_write(const float* rays_o, const float* rays_d, int64_t n_rays, const float* roi_host,
                       int32_t res, const uint8_t* binary, float step_size, const float* t_min,
-                      const float* t_max, const int32_t* offsets, int32_t* ray_idx, float* t_starts,
-                      float* t_ends, void* stream);
+                      const float* t_max, const int32_t* offsets, const void* runs, int32_t* ray_idx,
+                      float* t_starts, float* t_ends, void* stream);
 /* nerfacc OccupancyGrid.query_occ (visualization/visualization.py:214): occupancy 0/1 at points [n,3] */
 ANGIO_API int angio_grid_query(const float* points, int64_t n, const float* roi_host, int32_t res,
                      const uint8_t* binary, float* out, void* stream);

@@ -36,9 +36,10 @@ PROTOTYPES = {
     "angio_sample_rays": (c_i32, [c_ptr, c_i64, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "angio_raygen_flat": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_raygen": (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "angio_march_count": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_march_runs_bytes": (c_i64, [c_i64]),
+    "angio_march_count": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_exclusive_scan_i32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
-    "angio_march_write": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_march_write": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_grid_query": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
     "angio_visibility_mask": (c_i32, [c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_counts": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),

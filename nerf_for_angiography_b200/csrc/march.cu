@@ -79,9 +79,10 @@ struct Marcher {
   }
   __device__ __forceinline__ bool done() const { return !(tm < tmax); }
 
-  // emits at most `budget` samples through emit(t0, t1); returns the number emitted
-  template <class Emit>
-  __device__ __forceinline__ int advance(const MarchParams& p, const uint8_t* __restrict__ binary, int budget, Emit emit) {
+  // emits at most `budget` samples through emit(j, t0, t1); on_skip() is called whenever empty space is skipped (the next
+  // sample then starts a new run: its t0 no longer equals the previous t1).  Returns the number emitted.
+  template <class Emit, class Skip>
+  __device__ __forceinline__ int advance(const MarchParams& p, const uint8_t* __restrict__ binary, int budget, Emit emit, Skip on_skip) {
     int j = 0;
     while (tm < tmax && j < budget) {
       const float x = __fadd_rn(o[0], __fmul_rn(tm, d[0]));
@@ -105,6 +106,7 @@ struct Marcher {
         const float h = __fmul_rn(p.dt, 0.5f);
         t0 = __fsub_rn(tm, h);
         t1 = __fadd_rn(tm, h);
+        on_skip();
       }
     }
     return j;
@@ -112,12 +114,15 @@ struct Marcher {
 };
 
 struct Aabb6 { float v[6]; };
+constexpr int kMaxRuns = 8;   // recorded runs per ray (count pass -> write pass)
 
 __global__ void __launch_bounds__(128) march_count_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                                           int64_t n_rays, Aabb6 aabb, MarchParams p,
                                                           const uint8_t* __restrict__ binary, float near_plane,
                                                           float far_plane, float* __restrict__ t_min,
-                                                          float* __restrict__ t_max, int32_t* __restrict__ counts) {
+                                                          float* __restrict__ t_max, int32_t* __restrict__ counts,
+                                                          float* __restrict__ run_t0, float* __restrict__ run_t1,
+                                                          int32_t* __restrict__ run_n, int32_t* __restrict__ n_runs) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rays) return;
   float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
@@ -130,9 +135,36 @@ __global__ void __launch_bounds__(128) march_count_kernel(const float* __restric
   t_max[i] = b;
   Marcher m;
   m.init(o, d, a, b, p.dt);
-  int total = 0;
-  while (!m.done()) total += m.advance(p, binary, 1 << 30, [](int, float, float) {});
+  // Runs: maximal stretches of consecutive samples (t0 of a sample = t1 of the one before).  The first kMaxRuns of a ray are
+  // recorded (first sample's t0 and t1, length) so the write pass replays the fp32 t-chain without touching the grid again; a ray with more
+  // runs is flagged (n_runs = -1) and re-marched there.
+  int total = 0, nr = 0, cur = 0;
+  bool open = false;
+  while (!m.done())
+    total += m.advance(p, binary, 1 << 30,
+                       [&](int, float t0, float t1) {
+                         if (!open) {
+                           open = true;
+                           cur = 0;
+                           // the first sample of a run carries its own (t0, t1): t_min / t_min + dt at the ray start,
+                           // tm -+ dt/2 after a skip; from then on t0 = previous t1, t1 = t0 + dt
+                           if (run_t0 && nr < kMaxRuns) { run_t0[(int64_t)nr * n_rays + i] = t0; run_t1[(int64_t)nr * n_rays + i] = t1; }
+                         }
+                         ++cur;
+                       },
+                       [&]() {
+                         if (open) {
+                           if (run_n && nr < kMaxRuns) run_n[(int64_t)nr * n_rays + i] = cur;
+                           ++nr;
+                           open = false;
+                         }
+                       });
+  if (open) {
+    if (run_n && nr < kMaxRuns) run_n[(int64_t)nr * n_rays + i] = cur;
+    ++nr;
+  }
   counts[i] = total;
+  if (n_runs) n_runs[i] = nr <= kMaxRuns ? nr : -1;
 }
 
 constexpr int kStage = 32;            // samples staged per ray per round
@@ -142,7 +174,8 @@ constexpr int kWarpsPerBlock = 4;
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays, MarchParams p,
     const uint8_t* __restrict__ binary, const float* __restrict__ t_min, const float* __restrict__ t_max,
-    const int32_t* __restrict__ offsets, int32_t* __restrict__ ray_idx, float* __restrict__ t_starts,
+    const int32_t* __restrict__ offsets, const float* __restrict__ run_t0, const float* __restrict__ run_t1,
+    const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int32_t* __restrict__ ray_idx, float* __restrict__ t_starts,
     float* __restrict__ t_ends) {
   __shared__ float s_t0[kWarpsPerBlock][32][kStagePad];
   __shared__ float s_t1[kWarpsPerBlock][32][kStagePad];
@@ -153,20 +186,42 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
   const bool valid = i < n_rays;
   Marcher m;
   int written = 0, base = 0;
+  // replay state: run index, samples left in the current run, running t0
+  int nr = 0, run = 0, left = 0;
+  float rt0 = 0.0f, rt1 = 0.0f;
+  bool replay = false;
+  m.tm = 1.0f; m.tmax = 0.0f;  // done
   if (valid) {
-    float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
-    float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
-    m.init(o, d, t_min[i], t_max[i], p.dt);
     base = offsets[i];
-  } else {
-    m.tm = 1.0f; m.tmax = 0.0f;  // done
+    nr = n_runs ? n_runs[i] : -1;
+    replay = nr >= 0;
+    if (!replay) {             // no run table (or more than kMaxRuns runs): march this ray again
+      float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
+      float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
+      m.init(o, d, t_min[i], t_max[i], p.dt);
+    }
   }
   float(*st0)[kStagePad] = s_t0[warp];
   float(*st1)[kStagePad] = s_t1[warp];
-  while (__any_sync(0xffffffffu, !m.done())) {
+  while (__any_sync(0xffffffffu, !m.done() || (replay && (left > 0 || run < nr)))) {
     int cnt = 0;
-    if (!m.done())
-      cnt = m.advance(p, binary, kStage, [&](int j, float a, float b) { st0[lane][j] = a; st1[lane][j] = b; });
+    if (replay) {
+      // the same fp32 chain the marcher walks inside a run: t1 = t0 + dt, next t0 = t1
+      while (cnt < kStage && (left > 0 || run < nr)) {
+        if (left == 0) {
+          rt0 = run_t0[(int64_t)run * n_rays + i]; rt1 = run_t1[(int64_t)run * n_rays + i];
+          left = run_n[(int64_t)run * n_rays + i];
+          ++run;
+        }
+        st0[lane][cnt] = rt0; st1[lane][cnt] = rt1;
+        rt0 = rt1;
+        rt1 = __fadd_rn(rt0, p.dt);
+        --left;
+        ++cnt;
+      }
+    } else if (!m.done()) {
+      cnt = m.advance(p, binary, kStage, [&](int j, float a, float b) { st0[lane][j] = a; st1[lane][j] = b; }, []() {});
+    }
     __syncwarp();
     // cooperative flush: one ray segment at a time, 32 consecutive samples per store instruction
 #pragma unroll 1
@@ -243,6 +298,12 @@ __global__ void __launch_bounds__(256) grid_query_kernel(const float* __restrict
   out[i] = occupied_at(pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], p, binary) ? 1.0f : 0.0f;
 }
 
+// run table layout (angio_march_runs_bytes): [kMaxRuns][n_rays] float t0 | same for t1 | [kMaxRuns][n_rays] int32 length | [n_rays] int32 count
+float* run_table_t0(void* runs, int64_t n_rays) { (void)n_rays; return reinterpret_cast<float*>(runs); }
+float* run_table_t1(void* runs, int64_t n_rays) { return runs ? reinterpret_cast<float*>(runs) + (int64_t)kMaxRuns * n_rays : nullptr; }
+int32_t* run_table_n(void* runs, int64_t n_rays) { return runs ? reinterpret_cast<int32_t*>(runs) + 2 * (int64_t)kMaxRuns * n_rays : nullptr; }
+int32_t* run_table_count(void* runs, int64_t n_rays) { return runs ? reinterpret_cast<int32_t*>(runs) + 3 * (int64_t)kMaxRuns * n_rays : nullptr; }
+
 MarchParams make_params(const float* roi_host, int res, float dt) {
   MarchParams p;
   p.roi = angio::make_roi(roi_host);
@@ -258,16 +319,19 @@ MarchParams make_params(const float* roi_host, int res, float dt) {
 extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host,
                                  const float* roi_host, int32_t res, const uint8_t* binary, float near_plane,
                                  float far_plane, float step_size, float* t_min, float* t_max, int32_t* counts,
-                                 void* stream) {
+                                 void* runs, void* stream) {
   ANGIO_REQUIRE(rays_o && rays_d && aabb_host && roi_host && binary && t_min && t_max && counts, "angio_march_count: null pointer");
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_count: bad sizes (step_size must be > 0)");
   if (n_rays == 0) return 0;
   Aabb6 aabb;
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
   angio::note_launch(); march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
-      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts);
+      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts,
+      run_table_t0(runs, n_rays), run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays));
   return angio::finish_launch("angio_march_count");
 }
+
+extern "C" int64_t angio_march_runs_bytes(int64_t n_rays) { return n_rays < 0 ? ANGIO_ERR_INVALID_ARG : (3 * (int64_t)kMaxRuns + 1) * n_rays * 4; }
 
 extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out, void* stream) {
   ANGIO_REQUIRE(offsets && (counts || n == 0) && n >= 0, "angio_exclusive_scan_i32: bad arguments");
@@ -277,14 +341,17 @@ extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_
 
 extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64_t n_rays, const float* roi_host, int32_t res,
                                  const uint8_t* binary, float step_size, const float* t_min, const float* t_max,
-                                 const int32_t* offsets, int32_t* ray_idx, float* t_starts, float* t_ends, void* stream) {
+                                 const int32_t* offsets, const void* runs, int32_t* ray_idx, float* t_starts, float* t_ends,
+                                 void* stream) {
   ANGIO_REQUIRE(rays_o && rays_d && roi_host && binary && t_min && t_max && offsets && ray_idx && t_starts && t_ends,
                 "angio_march_write: null pointer");
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_write: bad sizes");
   if (n_rays == 0) return 0;
   const int rays_per_block = 32 * kWarpsPerBlock;
   angio::note_launch(); march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
-      rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets, ray_idx, t_starts, t_ends);
+      rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets,
+      run_table_t0(const_cast<void*>(runs), n_rays), run_table_t1(const_cast<void*>(runs), n_rays),
+      run_table_n(const_cast<void*>(runs), n_rays), run_table_count(const_cast<void*>(runs), n_rays), ray_idx, t_starts, t_ends);
   return angio::finish_launch("angio_march_write");
 }
 

@@ -124,13 +124,16 @@ def exclusive_scan(counts, total_out=None):
     return offsets
 
 
-def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size, capacity=None, total_out=None):
+def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size, capacity=None, total_out=None,
+          use_runs=True):
     """Two-pass occupancy-grid march.  Returns (ray_idx int32 [n], t_starts [n], t_ends [n], offsets int32 [R+1]).
 
     capacity=None: one host sync (reads the total sample count to size the outputs), like the reference library.
     capacity=C   : NO host sync -- the sample arrays have C entries, the first offsets[R] of which are valid; C must be an
                    upper bound (R * (ceil((far - near) / step) + 1) always is).  Downstream kernels read the count on the
                    device (offsets[R], also written to total_out when given).
+    use_runs: the count pass records each ray's runs of consecutive samples and the write pass replays them (no second grid
+              march); False re-marches in the write pass.  Bit-identical samples either way.
     """
     lib = _lib.load()
     rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
@@ -147,9 +150,10 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
     t_min = torch.empty((R,), dtype=torch.float32, device=dev)
     t_max = torch.empty((R,), dtype=torch.float32, device=dev)
     counts = torch.empty((R,), dtype=torch.int32, device=dev)
+    runs = torch.empty((int(lib.angio_march_runs_bytes(R)),), dtype=torch.uint8, device=dev) if use_runs else None
     _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
                                      float(near_plane), float(far_plane), float(step_size), _p(t_min), _p(t_max), _p(counts),
-                                     _stream()), "angio_march_count")
+                                     _p(runs), _stream()), "angio_march_count")
     offsets = exclusive_scan(counts, total_out)
     n = int(offsets[-1].item()) if capacity is None else int(capacity)
     ray_idx = torch.empty((n,), dtype=torch.int32, device=dev)
@@ -157,7 +161,7 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
     t1 = torch.empty((n,), dtype=torch.float32, device=dev)
     if n > 0:
         _lib.check(lib.angio_march_write(_p(rays_o), _p(rays_d), R, roi.ctypes.data, int(resolution), _p(binary), float(step_size),
-                                         _p(t_min), _p(t_max), _p(offsets), _p(ray_idx), _p(t0), _p(t1), _stream()),
+                                         _p(t_min), _p(t_max), _p(offsets), _p(runs), _p(ray_idx), _p(t0), _p(t1), _stream()),
                    "angio_march_write")
     return ray_idx, t0, t1, offsets
 

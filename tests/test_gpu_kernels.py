@@ -80,6 +80,9 @@ def _march_both(A, o, d, binary, res, near=1400.0, far=1600.0, n_steps=300, aabb
     tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, aabb, near, far)
     ri, ts, te, off = nerfacc_ref.march(o, d, tmin, tmax, aabb, res, binary, step)
     gi, g0, g1, goff = A.ops.march(_dev(o), _dev(d), aabb, aabb, res, _dev(binary), near, far, float(step))
+    # the write pass replays the runs recorded by the count pass (default) or marches the grid a second time: same samples
+    ni, n0, n1, noff = A.ops.march(_dev(o), _dev(d), aabb, aabb, res, _dev(binary), near, far, float(step), use_runs=False)
+    assert ni.equal(gi) and n0.equal(g0) and n1.equal(g1) and noff.equal(goff)
     # capacity mode (no host sync): same samples in the first offsets[R] slots, count left on the device
     cap = A.ops.march_capacity(len(o), near, far, float(step))
     tot = torch.zeros(1, dtype=torch.int32, device="cuda")
