@@ -431,12 +431,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         uint32_t pk[32];
         bias_relu_pack<false, true>(acc_tmem, consts + l * 128 + h * 64, nullptr, pk);
         tmem_st32(a_tmem + h * 32, pk);
-        if (TRAIN) {
+        signal_a_ready(&bars.a_ready[g], lane);
+        if (TRAIN) {   // after the hand-off: the tile-image / mask stores drain while the tensor core runs the next layer
           store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
           *reinterpret_cast<uint2*>(mask_base + (((int64_t)l * lay_tiles + tile) * kTile + row) * 16 + h * 8) =
               make_uint2(relu_bits16(pk), relu_bits16(pk + 16));
         }
-        signal_a_ready(&bars.a_ready[g], lane);
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, l, (int)(j / 2));
       }
       // ---- last hidden layer + output layer: logit = w_out . relu(z_{L+1}) + b_out on the CUDA cores, in fp32 before the
@@ -574,10 +574,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
           pk[c] = pack_bf16x2(gr * w2.x, gr * w2.y) & relu_word_mask(c < 16 ? mk.x : mk.y, c & 15);
         }
         tmem_st32(a_tmem, pk);
-        store_row_block(delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, row, pk);
-      }
-      if (n_stages > 0) {
-        signal_a_ready(&bars.a_ready[g], lane);
+        if (n_stages > 0) signal_a_ready(&bars.a_ready[g], lane);
+        store_row_block(delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, row, pk);   // drains behind the hand-off
       }
       // ---- hidden chain: delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}),  d = L+1 .. 2
       for (int st = 0; st < L; ++st) {
@@ -596,10 +594,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
           pk[16 + c] = pack_bf16x2(__uint_as_float(r1[2 * c]), __uint_as_float(r1[2 * c + 1])) & relu_word_mask(mk.y, c);
         }
         tmem_st32(a_tmem, pk);
-        store_row_block(delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}
-        if (st + 1 < n_stages) {
-          signal_a_ready(&bars.a_ready[g], lane);
-        }
+        if (st + 1 < n_stages) signal_a_ready(&bars.a_ready[g], lane);
+        store_row_block(delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}, drains behind the hand-off
       }
       // ---- feature gradient (delta_1 W_0) -> Fourier-coefficient gradient; half h reads feature columns [32h, 32h+32)
       if (enc) {

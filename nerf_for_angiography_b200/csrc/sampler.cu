@@ -92,14 +92,21 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const float* __r
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix;
-    for (int i0 = 0; i0 < m; i0 += kSelThreads) {
-      const int i = i0 + tid;
-      const uint32_t b = (i < m) ? kb[i] : 0u;
-      const bool hit = (i < m) && ((b & mask) == prefix);
-      // warp-aggregated histogram: the winning keys share their leading bits, so a plain atomicAdd serialises on one bin
-      const uint32_t digit = hit ? (b >> shift) & 255u : 256u;
-      const unsigned peers = __match_any_sync(0xffffffffu, digit);
-      if (hit && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+    for (int i0 = 0; i0 < m; i0 += 4 * kSelThreads) {
+      uint32_t b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                     // four independent loads in flight per thread
+        const int i = i0 + u * kSelThreads + tid;
+        b[u] = (i < m) ? kb[i] : 0xFFFFFFFFu;           // keys are finite positive floats: never all ones
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool hit = (b[u] != 0xFFFFFFFFu) && ((b[u] & mask) == prefix);
+        // warp-aggregated histogram: the winning keys share their leading bits, so a plain atomicAdd serialises on one bin
+        const uint32_t digit = hit ? (b[u] >> shift) & 255u : 256u;
+        const unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (hit && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+      }
     }
     __syncthreads();
     if (tid < 32) {                                          // warp 0 finds the digit that holds the s_need-th key
