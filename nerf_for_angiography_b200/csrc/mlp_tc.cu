@@ -52,6 +52,7 @@ constexpr float kTwoPi = 6.2831855f;
 constexpr int kA0Bytes = 16384;    // a_0 tile image: [128 rows x 64 cols] bf16
 constexpr int kActBytes = 32768;   // a_d / delta_d tile image: two [128 x 64] blocks
 constexpr int kMaskBytes = 2048;   // ReLU bit mask of one a_d tile: [128 rows][4 x 32 bits]
+constexpr int kStageBytesTotal = 65536;   // 16 epilogue warps x 4 KB of tile-image staging (training kernels)
 
 struct TcPlan {
   int n_hidden;     // L: number of 128x128 layers
@@ -62,6 +63,7 @@ struct TcPlan {
   int off_const;    // byte offset of the fp32 constant block
   int n_const;      // floats in the constant block
   int total_bytes;  // packed image size (multiple of 16)
+  int stage_off;    // byte offset of the 64 KB tile-image staging area behind the image (training kernels), 0 = does not fit
 };
 
 __host__ __device__ inline int w_offset(int w) { return w == 0 ? 0 : 16384 + (w - 1) * 32768; }
@@ -78,6 +80,8 @@ inline bool make_plan(const MlpLayout& L, TcPlan* p) {
   // biases (L+1) x 128 | w_out 128 | b_out (padded to 4) | coef (padded to 4)
   p->n_const = (L.n_hidden + 2) * 128 + 4 + (3 * L.basis + 3) / 4 * 4;
   p->total_bytes = (p->off_const + p->n_const * 4 + 15) / 16 * 16;
+  p->stage_off = (p->total_bytes + 1023) / 1024 * 1024;
+  if (p->stage_off + kStageBytesTotal + 2048 > 227 * 1024) p->stage_off = 0;
   return p->total_bytes + 2048 <= 227 * 1024;
 }
 
@@ -205,6 +209,29 @@ __device__ __forceinline__ void store_row_block(uint8_t* __restrict__ block, int
     *reinterpret_cast<uint4*>(base + ((c ^ (row & 7)) << 4)) = v;
   }
 }
+// Tile-image rows of one warp (32 rows x 128 B = 4 KB, contiguous in the image) through shared memory and the TMA unit:
+// each lane drops its swizzled row into the warp's staging buffer (conflict-free: the XOR swizzle spreads 8 rows over the 8
+// chunk positions), one lane issues a single 4 KB bulk copy.  Direct global stores cost eight 16-byte STG per thread, each warp
+// instruction touching 32 different 128-byte lines -- the LSU, not HBM, was the limit of the training kernels.
+// `stage` == nullptr (weight image too large to leave room) falls back to the direct stores.
+constexpr int kStageBytesPerWarp = 4096;
+__device__ __forceinline__ void store_rows_staged(uint8_t* __restrict__ stage, uint8_t* __restrict__ gdst_block, int quadrant, int row,
+                                                  int lane, const uint32_t (&pk)[32]) {
+  if (stage == nullptr) { store_row_block(gdst_block, row, pk); return; }
+  if (lane == 0) bulk_wait_read<0>();           // the previous bulk copy out of this buffer has been read
+  __syncwarp();
+  uint8_t* base = stage + lane * 128;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+    *reinterpret_cast<uint4*>(base + ((c ^ (lane & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    bulk_s2g(gdst_block + quadrant * kStageBytesPerWarp, stage, kStageBytesPerWarp);
+    bulk_commit();
+  }
+}
+
 // ReLU bit masks: the training forward leaves, next to every activation tile image, one bit per element (a > 0), 16 bytes
 // per row instead of 256, so the data-gradient chain never re-reads the activations (1.2 KB/sample of HBM reads saved).
 // 16 consecutive bf16x2 words -> 32 bits: bit k = low element of word k, bit 16 + k = high element.  Post-ReLU values are
@@ -371,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
     const float b_out = consts[(P.n_hidden + 2) * 128];
     const float* w_out = consts + (P.n_hidden + 1) * 128 + h * 64;   // fp32 output weights of this warp's columns
     const int pair_bar = 1 + g * 4 + q;           // named barrier shared by the two column-half warps of this row quadrant
+    uint8_t* stage = (TRAIN && P.stage_off > 0) ? smem + P.stage_off + (warp - 2) * kStageBytesPerWarp : nullptr;
     uint8_t* mask_base = TRAIN ? saved + lay_tiles * kA0Bytes + (int64_t)(P.n_hidden + 1) * lay_tiles * kActBytes : nullptr;
     const int nb = 3 * P.basis;
     uint32_t phase = 0;
@@ -433,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         tmem_st32(a_tmem + h * 32, pk);
         signal_a_ready(&bars.a_ready[g], lane);
         if (TRAIN) {   // after the hand-off: the tile-image / mask stores drain while the tensor core runs the next layer
-          store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+          store_rows_staged(stage, saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, q, row, lane, pk);
           *reinterpret_cast<uint2*>(mask_base + (((int64_t)l * lay_tiles + tile) * kTile + row) * 16 + h * 8) =
               make_uint2(relu_bits16(pk), relu_bits16(pk + 16));
         }
@@ -462,7 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         const float dot = bias_relu_math<true, TRAIN>(r0, r1, consts + l * 128 + h * 64, w_out, pk);
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, 6, (int)(j / 2));
         if (TRAIN) {
-          store_row_block(saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, row, pk);
+          store_rows_staged(stage, saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, q, row, lane, pk);
           *reinterpret_cast<uint2*>(mask_base + (((int64_t)l * lay_tiles + tile) * kTile + row) * 16 + h * 8) =
               make_uint2(relu_bits16(pk), relu_bits16(pk + 16));
         }
@@ -477,6 +505,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(3, g, l, (int)(j / 2));
       }
     }
+    if (TRAIN && stage != nullptr && lane == 0) bulk_wait<0>();   // our bulk stores have left shared memory and are complete
   }
   fence_before_sync();
   __syncthreads();
@@ -558,6 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
     // ReLU bits of a_d (d >= 1), row r, column half h: mask_base + (((d-1) * lay_tiles + tile) * 128 + r) * 16 + 8 h
     const uint8_t* mask_base = saved + lay_tiles * kA0Bytes + (int64_t)(L + 1) * lay_tiles * kActBytes + row * 16 + h * 8;
     uint8_t* delta_h = delta + h * 16384;
+    uint8_t* stage = P.stage_off > 0 ? smem + P.stage_off + (warp - 2) * kStageBytesPerWarp : nullptr;
     uint32_t phase = 0;
     for (int64_t j = g; j < my_tiles; j += 2) {
       const int64_t tile = blockIdx.x + j * gridDim.x;
@@ -575,7 +605,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
         }
         tmem_st32(a_tmem, pk);
         if (n_stages > 0) signal_a_ready(&bars.a_ready[g], lane);
-        store_row_block(delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, row, pk);   // drains behind the hand-off
+        store_rows_staged(stage, delta_h + ((int64_t)L * lay_tiles + tile) * kActBytes, q, row, lane, pk);   // drains behind the hand-off
       }
       // ---- hidden chain: delta_{d-1} = (delta_d W_{d-1}) * relu'(a_{d-1}),  d = L+1 .. 2
       for (int st = 0; st < L; ++st) {
@@ -595,7 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
         }
         tmem_st32(a_tmem, pk);
         if (st + 1 < n_stages) signal_a_ready(&bars.a_ready[g], lane);
-        store_row_block(delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, row, pk);   // delta_{d-1}, drains behind the hand-off
+        store_rows_staged(stage, delta_h + ((int64_t)(d - 2) * lay_tiles + tile) * kActBytes, q, row, lane, pk);   // delta_{d-1}, drains behind the hand-off
       }
       // ---- feature gradient (delta_1 W_0) -> Fourier-coefficient gradient; half h reads feature columns [32h, 32h+32)
       if (enc) {
@@ -634,6 +664,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t
         }
       }
     }
+    if (stage != nullptr && lane == 0) bulk_wait<0>();   // our bulk stores are complete before the CTA gives up its shared memory
     // ---- per-CTA reduction of the coefficient gradient (fixed order)
     if (enc) {
 #pragma unroll
@@ -917,7 +948,7 @@ static int ensure_smem(K kernel, size_t smem, size_t* cached) {
 
 template <int MODE, bool TRAIN>
 static int launch_fwd(const TcPlan& P, const void* packed, const angio_samples& in, float* out, void* saved, cudaStream_t st) {
-  const size_t smem = (size_t)P.total_bytes + 1024;
+  const size_t smem = (TRAIN && P.stage_off > 0) ? (size_t)P.stage_off + kStageBytesTotal + 1024 : (size_t)P.total_bytes + 1024;
   static size_t cached = 0;
   if (int rc = ensure_smem(mlp_fwd_tc_kernel<MODE, TRAIN>, smem, &cached)) return rc;
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
@@ -977,7 +1008,7 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
 
   // (2) data-gradient chain
   {
-    const size_t smem = (size_t)P.total_bytes + 1024;
+    const size_t smem = P.stage_off > 0 ? (size_t)P.stage_off + kStageBytesTotal + 1024 : (size_t)P.total_bytes + 1024;
     static size_t cached = 0;
     if (int rc = ensure_smem(mlp_dgrad_tc_kernel, smem, &cached)) return rc;
     int grid = sm_count();
