@@ -31,9 +31,11 @@ WORKLOADS = {
     # name: (img_size, n_views(theta sweep), rays/GPU/step, volume_res, hidden layers, width, pos_enc)
     "config3": dict(img=512, thetas=[6.0 * i for i in range(60)], rays=65536, vol=256, L=4, H=128, enc="fourier"),
     "config2": dict(img=256, thetas=[0.0, 45.0, 90.0, 135.0], rays=65536, vol=256, L=4, H=128, enc="fourier"),
+    # BASELINE configs[3]: 1024^2 x 120 views, 8x256 MLP.  Width 256 has no tcgen05 kernel yet: fp32 path.
+    "config4": dict(img=1024, thetas=[3.0 * i for i in range(120)], rays=131072, vol=256, L=8, H=256, enc="fourier", precision="fp32"),
     "tiny": dict(img=64, thetas=[22.5 * i for i in range(8)], rays=4096, vol=64, L=4, H=128, enc="fourier"),
 }
-MLP_FWD_FLOP = {("fourier", 4, 128): 139776, ("none", 4, 128): 132096}
+MLP_FWD_FLOP = {("fourier", 4, 128): 139776, ("none", 4, 128): 132096, ("fourier", 8, 256): 1065984}
 
 
 def model_def(w, device, precision):
@@ -182,6 +184,8 @@ def main():
                          "two-phase pass with early ray termination; the kept samples are bit-identical either way")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if "precision" in w:
+        args.precision = w["precision"]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
