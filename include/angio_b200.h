@@ -100,8 +100,10 @@ ANGIO_API int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t
 /* pass 2: write samples.  ray_idx [n] int32, t_starts / t_ends [n] float32 */
 ANGIO_API int angio_march_write(const float* rays_o, const float* rays_d, int64_t n_rays, const float* roi_host,
                       int32_t res, const uint8_t* binary, float step_size, const float* t_min,
-                      const float* t_max, const int32_t* offsets, const void* runs, int32_t* ray_idx,
-                      float* t_starts, float* t_ends, void* stream);
+                      const float* t_max, const int32_t* offsets, const void* runs, int64_t capacity,
+                      int32_t* ray_idx, float* t_starts, float* t_ends, void* stream);
+/* capacity (here and in angio_compact_samples): number of elements the output arrays hold; samples beyond it are dropped
+ * instead of written (0 = unchecked).  The sync-free callers size the arrays by an upper bound and never hit it. */
 /* nerfacc OccupancyGrid.query_occ (visualization/visualization.py:214): occupancy 0/1 at points [n,3] */
 ANGIO_API int angio_grid_query(const float* points, int64_t n, const float* roi_host, int32_t res,
                      const uint8_t* binary, float* out, void* stream);
@@ -131,7 +133,7 @@ ANGIO_API int angio_ray_segment_ids(const int32_t* offsets, const int32_t* seg_o
 ANGIO_API int angio_visibility_head(const float* alphas, const int32_t* offsets, int64_t n_rays, int32_t k0,
                           float early_stop_eps, uint8_t* alive, void* stream);
 ANGIO_API int angio_compact_samples(const uint8_t* keep, const int32_t* offsets, const int32_t* new_offsets,
-                          int64_t n_rays, const float* t_starts, const float* t_ends,
+                          int64_t n_rays, const float* t_starts, const float* t_ends, int64_t capacity,
                           int32_t* ray_idx_out, float* t_starts_out, float* t_ends_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -39,13 +39,13 @@ PROTOTYPES = {
     "angio_march_runs_bytes": (c_i64, [c_i64]),
     "angio_march_count": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_exclusive_scan_i32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
-    "angio_march_write": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_march_write": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_grid_query": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
     "angio_visibility_mask": (c_i32, [c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_counts": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_ids": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     "angio_visibility_head": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_f32, c_ptr, c_ptr]),
-    "angio_compact_samples": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_compact_samples": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_mlp_param_count": (c_i64, [_P_DESC]),
     "angio_mlp_input_width": (c_i32, [_P_DESC]),
     "angio_mlp_workspace_bytes": (c_i64, [_P_DESC, c_i64, c_i32, c_i32]),

@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays, MarchParams p,
     const uint8_t* __restrict__ binary, const float* __restrict__ t_min, const float* __restrict__ t_max,
     const int32_t* __restrict__ offsets, const float* __restrict__ run_t0, const float* __restrict__ run_t1,
-    const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int32_t* __restrict__ ray_idx, float* __restrict__ t_starts,
-    float* __restrict__ t_ends) {
+    const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int64_t capacity, int32_t* __restrict__ ray_idx,
+    float* __restrict__ t_starts, float* __restrict__ t_ends) {
   __shared__ float s_t0[kWarpsPerBlock][32][kStagePad];
   __shared__ float s_t1[kWarpsPerBlock][32][kStagePad];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
       const int c = __shfl_sync(0xffffffffu, cnt, r);
       if (c == 0) continue;
       const int dst = __shfl_sync(0xffffffffu, base + written, r);
-      if (lane < c) {
+      if (lane < c && (int64_t)dst + lane < capacity) {   // never write past the caller's arrays
         ray_idx[dst + lane] = (int32_t)(ray0 + r);
         t_starts[dst + lane] = st0[r][lane];
         t_ends[dst + lane] = st1[r][lane];
@@ -380,8 +380,8 @@ extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_
 
 extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64_t n_rays, const float* roi_host, int32_t res,
                                  const uint8_t* binary, float step_size, const float* t_min, const float* t_max,
-                                 const int32_t* offsets, const void* runs, int32_t* ray_idx, float* t_starts, float* t_ends,
-                                 void* stream) {
+                                 const int32_t* offsets, const void* runs, int64_t capacity, int32_t* ray_idx, float* t_starts,
+                                 float* t_ends, void* stream) {
   ANGIO_REQUIRE(rays_o && rays_d && roi_host && binary && t_min && t_max && offsets && ray_idx && t_starts && t_ends,
                 "angio_march_write: null pointer");
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_write: bad sizes");
@@ -390,7 +390,8 @@ extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64
   angio::note_launch(); march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets,
       run_table_t0(const_cast<void*>(runs), n_rays), run_table_t1(const_cast<void*>(runs), n_rays),
-      run_table_n(const_cast<void*>(runs), n_rays), run_table_count(const_cast<void*>(runs), n_rays), ray_idx, t_starts, t_ends);
+      run_table_n(const_cast<void*>(runs), n_rays), run_table_count(const_cast<void*>(runs), n_rays),
+      capacity > 0 ? capacity : INT64_MAX, ray_idx, t_starts, t_ends);
   return angio::finish_launch("angio_march_write");
 }
 

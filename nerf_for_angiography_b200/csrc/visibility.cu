@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) visibility_mask_kernel(const float* __res
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict__ keep, const int32_t* __restrict__ offsets,
                                                       const int32_t* __restrict__ new_offsets, int64_t n_rays,
                                                       const float* __restrict__ t_starts, const float* __restrict__ t_ends,
-                                                      int32_t* __restrict__ ray_idx_out, float* __restrict__ t0_out,
+                                                      int64_t capacity, int32_t* __restrict__ ray_idx_out, float* __restrict__ t0_out,
                                                       float* __restrict__ t1_out) {
   const int lane = threadIdx.x % 32;
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
@@ -69,9 +69,11 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict_
       const unsigned m = __ballot_sync(0xffffffffu, k);
       if (k) {
         const int pos = dst + __popc(m & ((1u << lane) - 1u));
-        ray_idx_out[pos] = (int32_t)r;
-        t0_out[pos] = t_starts[i];
-        t1_out[pos] = t_ends[i];
+        if (pos < capacity) {                     // never write past the caller's arrays
+          ray_idx_out[pos] = (int32_t)r;
+          t0_out[pos] = t_starts[i];
+          t1_out[pos] = t_ends[i];
+        }
       }
       dst += __popc(m);
       if (dst == dst_end) break;   // every kept sample of this ray has been written
@@ -165,11 +167,11 @@ extern "C" int angio_visibility_head(const float* alphas, const int32_t* offsets
 }
 
 extern "C" int angio_compact_samples(const uint8_t* keep, const int32_t* offsets, const int32_t* new_offsets, int64_t n_rays,
-                                     const float* t_starts, const float* t_ends, int32_t* ray_idx_out, float* t_starts_out,
-                                     float* t_ends_out, void* stream) {
+                                     const float* t_starts, const float* t_ends, int64_t capacity, int32_t* ray_idx_out,
+                                     float* t_starts_out, float* t_ends_out, void* stream) {
   ANGIO_REQUIRE(offsets && new_offsets && n_rays >= 0, "angio_compact_samples: bad arguments");
   if (n_rays == 0) return 0;
   angio::note_launch(); compact_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(keep, offsets, new_offsets, n_rays, t_starts, t_ends,
-                                                                         ray_idx_out, t_starts_out, t_ends_out);
+                                                                         capacity > 0 ? capacity : INT64_MAX, ray_idx_out, t_starts_out, t_ends_out);
   return angio::finish_launch("angio_compact_samples");
 }

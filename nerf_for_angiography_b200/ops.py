@@ -161,7 +161,7 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
     t1 = torch.empty((n,), dtype=torch.float32, device=dev)
     if n > 0:
         _lib.check(lib.angio_march_write(_p(rays_o), _p(rays_d), R, roi.ctypes.data, int(resolution), _p(binary), float(step_size),
-                                         _p(t_min), _p(t_max), _p(offsets), _p(runs), _p(ray_idx), _p(t0), _p(t1), _stream()),
+                                         _p(t_min), _p(t_max), _p(offsets), _p(runs), n, _p(ray_idx), _p(t0), _p(t1), _stream()),
                    "angio_march_write")
     return ray_idx, t0, t1, offsets
 
@@ -229,7 +229,7 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     t0 = torch.empty((n2,), dtype=torch.float32, device=dev)
     t1 = torch.empty((n2,), dtype=torch.float32, device=dev)
     if n2 > 0:
-        _lib.check(lib.angio_compact_samples(_p(keep), _p(offsets), _p(new_offsets), R, _p(t_starts), _p(t_ends), _p(ray_idx), _p(t0),
+        _lib.check(lib.angio_compact_samples(_p(keep), _p(offsets), _p(new_offsets), R, _p(t_starts), _p(t_ends), n2, _p(ray_idx), _p(t0),
                                              _p(t1), _stream()), "angio_compact_samples")
     return ray_idx, t0, t1, new_offsets, (keep if host_totals is None else host_totals)
 
