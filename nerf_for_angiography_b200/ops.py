@@ -43,6 +43,14 @@ def _host6(v, name):
     return a
 
 
+def _alloc(pool, key, n, dtype, device):
+    """n elements: a fresh tensor, or -- with a BufferPool -- a view of the pooled buffer `key` (valid until the next request
+    for the same key; the sync-free training loop uses this so that a steady-state step never touches the CUDA allocator)."""
+    if pool is None:
+        return torch.empty((int(n),), dtype=dtype, device=device)
+    return pool.typed(key, int(n), dtype, device)
+
+
 def sm_count() -> int:
     return int(_lib.load().angio_sm_count())
 
@@ -125,7 +133,7 @@ def exclusive_scan(counts, total_out=None):
 
 
 def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size, capacity=None, total_out=None,
-          use_runs=True):
+          use_runs=True, pool=None, tag="march"):
     """Two-pass occupancy-grid march.  Returns (ray_idx int32 [n], t_starts [n], t_ends [n], offsets int32 [R+1]).
 
     capacity=None: one host sync (reads the total sample count to size the outputs), like the reference library.
@@ -150,15 +158,15 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
     t_min = torch.empty((R,), dtype=torch.float32, device=dev)
     t_max = torch.empty((R,), dtype=torch.float32, device=dev)
     counts = torch.empty((R,), dtype=torch.int32, device=dev)
-    runs = torch.empty((int(lib.angio_march_runs_bytes(R)),), dtype=torch.uint8, device=dev) if use_runs else None
+    runs = _alloc(pool, tag + "_runs", int(lib.angio_march_runs_bytes(R)), torch.uint8, dev) if use_runs else None
     _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
                                      float(near_plane), float(far_plane), float(step_size), _p(t_min), _p(t_max), _p(counts),
                                      _p(runs), _stream()), "angio_march_count")
     offsets = exclusive_scan(counts, total_out)
     n = int(offsets[-1].item()) if capacity is None else int(capacity)
-    ray_idx = torch.empty((n,), dtype=torch.int32, device=dev)
-    t0 = torch.empty((n,), dtype=torch.float32, device=dev)
-    t1 = torch.empty((n,), dtype=torch.float32, device=dev)
+    ray_idx = _alloc(pool, tag + "_idx", n, torch.int32, dev)
+    t0 = _alloc(pool, tag + "_t0", n, torch.float32, dev)
+    t1 = _alloc(pool, tag + "_t1", n, torch.float32, dev)
     if n > 0:
         _lib.check(lib.angio_march_write(_p(rays_o), _p(rays_d), R, roi.ctypes.data, int(resolution), _p(binary), float(step_size),
                                          _p(t_min), _p(t_max), _p(offsets), _p(runs), n, _p(ray_idx), _p(t0), _p(t1), _stream()),
@@ -195,7 +203,7 @@ def grid_query(points, roi_aabb, resolution, binary):
 
 
 # ------------------------------------------------------------------------------------------------ visibility
-def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None, capacity=None):
+def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None, capacity=None, pool=None):
     """Visibility mask + compaction.  Returns (ray_idx', t_starts', t_ends', offsets', keep).
 
     alphas / t_starts / t_ends may be capacity-sized (see `march`): only the ranges named by `offsets` are touched.
@@ -210,7 +218,7 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     t_starts = _chk(t_starts, torch.float32, "t_starts", 1)
     t_ends = _chk(t_ends, torch.float32, "t_ends", 1)
     R, n, dev = offsets.numel() - 1, alphas.numel(), alphas.device
-    keep = torch.empty((n,), dtype=torch.uint8, device=dev)
+    keep = _alloc(pool, "vis_keep", n, torch.uint8, dev)
     kept = torch.empty((R,), dtype=torch.int32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(alphas), _p(offsets), R, float(early_stop_eps), float(alpha_thre), _p(keep), _p(kept),
                                          _stream()), "angio_visibility_mask")
@@ -225,16 +233,17 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     else:
         new_offsets = exclusive_scan(kept)
         n2 = int(new_offsets[-1].item())
-    ray_idx = torch.empty((n2,), dtype=torch.int32, device=dev)
-    t0 = torch.empty((n2,), dtype=torch.float32, device=dev)
-    t1 = torch.empty((n2,), dtype=torch.float32, device=dev)
+    ray_idx = _alloc(pool, "kept_idx", n2, torch.int32, dev)
+    t0 = _alloc(pool, "kept_t0", n2, torch.float32, dev)
+    t1 = _alloc(pool, "kept_t1", n2, torch.float32, dev)
     if n2 > 0:
         _lib.check(lib.angio_compact_samples(_p(keep), _p(offsets), _p(new_offsets), R, _p(t_starts), _p(t_ends), n2, _p(ray_idx), _p(t0),
                                              _p(t1), _stream()), "angio_compact_samples")
     return ray_idx, t0, t1, new_offsets, (keep if host_totals is None else host_totals)
 
 
-def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t_starts, t_ends, offsets, early_stop_eps, k0=32, timing=None):
+def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t_starts, t_ends, offsets, early_stop_eps, k0=32, timing=None,
+                     pool=None):
     """alpha_fn over the marched samples with early ray termination (see angio_b200.h "Two-phase visibility pass"):
     phase A = the first k0 samples of every ray, phase B = the rest of the rays whose transmittance is still >= early_stop_eps
     after them.  Entries of the returned alphas behind a ray's termination point are undefined; visibility_compact never
@@ -245,7 +254,7 @@ def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t
     offsets = _chk(offsets, torch.int32, "offsets", 1)
     R, dev = offsets.numel() - 1, offsets.device
     cap = t_starts.numel()
-    alphas = torch.empty((cap,), dtype=torch.float32, device=dev)
+    alphas = _alloc(pool, "vis_alphas", cap, torch.float32, dev)
     evaluated = torch.zeros((2,), dtype=torch.int32, device=dev)
     counts = torch.empty((R,), dtype=torch.int32, device=dev)
     alive = torch.empty((R,), dtype=torch.uint8, device=dev)
@@ -253,13 +262,13 @@ def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t
     for phase, (skip, limit, mask, size) in enumerate(((0, k0, None, min(cap, R * k0)), (k0, -1, alive, cap))):
         _lib.check(lib.angio_ray_segment_counts(_p(offsets), R, skip, limit, _p(mask), _p(counts), _stream()), "angio_ray_segment_counts")
         seg = exclusive_scan(counts, evaluated[phase:phase + 1])
-        ids = torch.empty((size,), dtype=torch.int32, device=dev)
+        ids = _alloc(pool, "vis_ids%d" % phase, size, torch.int32, dev)
         if size > 0:
             _lib.check(lib.angio_ray_segment_ids(_p(offsets), _p(seg), R, skip, _p(ids), _stream()), "angio_ray_segment_ids")
             if timing is not None:                         # bench.py: CUDA events around each MLP launch + its device sample count
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            mlp_forward(desc, params, packed, OUT_ALPHA, precision, out=alphas, sample_idx=ids, n_dev=seg[R:R + 1], **kw)
+            mlp_forward(desc, params, packed, OUT_ALPHA, precision, out=alphas, sample_idx=ids, n_dev=seg[R:R + 1], pool=pool, **kw)
             if timing is not None:
                 ev1.record()
                 timing.append((ev0, ev1, evaluated[phase:phase + 1]))
@@ -294,14 +303,14 @@ def composite_backward(logits, t_starts, t_ends, offsets, pix, grad_pix, zero_ma
     return g
 
 
-def composite_mse_fused(logits, t_starts, t_ends, offsets, target, n_rays_total=None):
+def composite_mse_fused(logits, t_starts, t_ends, offsets, target, n_rays_total=None, pool=None):
     """Returns (pix[R], grad_logits[n], loss_sum[1])."""
     lib = _lib.load()
     logits = _chk(logits, torch.float32, "predictions", 1)
     target = _chk(target, torch.float32, "target", 1)
     R = offsets.numel() - 1
     pix = torch.empty((R,), dtype=torch.float32, device=logits.device)
-    g = torch.empty_like(logits)
+    g = _alloc(pool, "glogits", logits.numel(), torch.float32, logits.device)
     loss = torch.zeros((1,), dtype=torch.float32, device=logits.device)
     _lib.check(lib.angio_composite_mse_fused(_p(logits), _p(t_starts), _p(t_ends), _p(offsets), R, _p(target),
                                              int(n_rays_total or R), _p(pix), _p(g), _p(loss), _stream()), "angio_composite_mse_fused")
@@ -357,6 +366,9 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
     return s, n
 
 
+_ITEMSIZE = {torch.float32: 4, torch.int32: 4, torch.uint8: 1, torch.int64: 8, torch.float64: 8}
+
+
 class BufferPool:
     """Grow-only device scratch buffers (saved activations / workspaces / sample arrays) so steady-state steps never hit
     cudaMalloc.  A buffer that must grow doubles (the kept-sample count rises steadily while a model trains; a 1.3x policy
@@ -383,7 +395,7 @@ class BufferPool:
 
     def typed(self, key, n, dtype, device):
         """n elements of dtype carved from the pooled buffer `key`."""
-        item = torch.empty((), dtype=dtype).element_size()
+        item = _ITEMSIZE[dtype]
         return self.get(key, n * item, device)[:n * item].view(dtype)
 
 
@@ -397,7 +409,7 @@ def mlp_forward(desc, params, packed, out_mode, precision, saved=False, pool=Non
     dev = params.device
     if out is None:
         n_out = sample_kw["t_starts"].numel() if sample_kw.get("sample_idx") is not None else n
-        out = torch.empty((n_out,), dtype=torch.float32, device=dev)
+        out = _alloc(pool if saved else None, "logits", n_out, torch.float32, dev)   # pooled only on the training path
     else:
         out = _chk(out, torch.float32, "out", 1)
     saved_buf = None

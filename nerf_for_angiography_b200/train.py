@@ -76,6 +76,9 @@ class Trainer:
         self.last = {}
         self.kernel_events = None     # bench.py: list of (start event, end event, sample count) per visibility-pass MLP launch
         self.sync_free = self._plan_memory(sync_free, memory_fraction)
+        self.prefetch = True          # draw + march the next batch under the gradient all-reduce (sync-free mode)
+        self._prefetched = None
+        self._march_calls = 0
         # visibility pass with early ray termination (bf16 path): number of leading samples per ray evaluated before the rays
         # that are already opaque are dropped (multiple of 32); 0 / None = evaluate every marched sample like the reference
         self.early_termination = int(early_termination) if early_termination else 0
@@ -108,11 +111,36 @@ class Trainer:
 
     def update_grids(self):
         """acc_update_n_step for both grids (run_nerf_acc.py:285-286)."""
-        self.acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.alpha_thre, generator=self.grid_gen)
+        self.acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.alpha_thre, n=self.GRID_EVERY, generator=self.grid_gen)
         if self.vessel_acc_grid is not None:
-            self.vessel_acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.vessel_alpha_thre, generator=self.grid_gen)
+            self.vessel_acc_grid.every_n_step(self.n_iter, self._occ_eval, occ_thre=self.vessel_alpha_thre, n=self.GRID_EVERY,
+                                              generator=self.grid_gen)
 
-    def march_and_filter(self, o, d, totals=None, sync_free=None):
+    GRID_EVERY = 16     # nerfacc's every_n_step default (the reference does not override it)
+
+    def _march(self, o, d, totals, pooled=True):
+        """Marcher only (bf16 path: capacity-sized arrays, count left on the device in offsets[R] and totals[0])."""
+        g = self.acc_grid
+        bf16 = self.model._precision_id == ops.PREC_BF16
+        cap = ops.march_capacity(o.shape[0], self.near, self.far, self.step_size) if bf16 else None
+        # sync-free mode: pooled arrays, two alternating sets because a prefetched batch is alive next to the current one
+        pool, tag = None, "march"
+        if pooled and self.sync_free and o.shape[0] <= self.n_rays:
+            pool, tag = self.pool_bufs, "march%d" % (self._march_calls % 2)
+            self._march_calls += 1
+        return ops.march(o, d, self._aabb_host, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far, self.step_size,
+                         capacity=cap, total_out=totals[0:1] if bf16 else None, pool=pool, tag=tag)
+
+    def _draw(self, march):
+        """Next ray batch from the pool (+ its march when the occupancy grid will not change before it is used)."""
+        totals = torch.zeros((4,), dtype=torch.int32, device=self.dev)     # [marched, kept, sampler candidates, sampler overflow]
+        stream = self.pool._seed_streams.get(id(self.ray_gen))
+        pre_state = stream.bit_generator.state if stream is not None else None   # a checkpoint taken while this batch is pending re-draws it
+        o, d, target = self.pool.sample(self.n_rays, generator=self.ray_gen, status=totals[2:4])
+        return dict(o=o, d=d, target=target, totals=totals, marched=self._march(o, d, totals) if march else None, pre_state=pre_state,
+                    had_stream=stream is not None)
+
+    def march_and_filter(self, o, d, totals=None, sync_free=None, marched=None):
         """acc_ray_marching (run_nerf_acc.py:287): returns (ray_idx int32, t0, t1, offsets, n_prefilter).
 
         fp32 check path: exact-size arrays, two host syncs (marched and kept counts), like the reference library.
@@ -127,14 +155,14 @@ class Trainer:
         cap = ops.march_capacity(R, self.near, self.far, self.step_size) if bf16 else None
         if bf16 and totals is None:
             totals = torch.zeros((4,), dtype=torch.int32, device=o.device)
-        ray_idx, t0, t1, offsets = ops.march(o, d, self._aabb_host, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far,
-                                             self.step_size, capacity=cap, total_out=totals[0:1] if bf16 else None)
+        ray_idx, t0, t1, offsets = marched if marched is not None else self._march(o, d, totals, pooled=sync_free)
         n_pre = ray_idx.numel()
         if n_pre > 0:
             if bf16 and self.early_termination:
                 # same kept set as evaluating every sample; only samples that can still be visible reach the MLP
                 alphas, _ = ops.alphas_two_phase(self.model._desc, self.flat, self.packed, self.model._precision_id, o, d, ray_idx,
-                                                 t0, t1, offsets, self.early_stop_eps, k0=self.early_termination, timing=self.kernel_events)
+                                                 t0, t1, offsets, self.early_stop_eps, k0=self.early_termination, timing=self.kernel_events,
+                                                 pool=self.pool_bufs if sync_free else None)
             else:
                 if self.kernel_events is not None:
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -148,7 +176,8 @@ class Trainer:
             thre = min(self.alpha_thre, g.occs_mean_host)
             ray_idx, t0, t1, offsets, host_totals = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre,
                                                                           totals=totals if bf16 else None,
-                                                                          capacity=cap if sync_free else None)
+                                                                          capacity=cap if sync_free else None,
+                                                                          pool=self.pool_bufs if sync_free else None)
             if sync_free:
                 n_pre = None
             elif bf16:
@@ -165,20 +194,29 @@ class Trainer:
     def step(self, rays=None):
         """rays: optional (o[R,3], d[R,3], target[R]) -- otherwise sampled from the pool.  Returns a StepResult: `loss` is a
         device scalar, the sample counts are fetched lazily.  In sync-free mode nothing in here waits for the GPU (except the
-        occupancy-grid refresh every 16th iteration, which reads mean(occs))."""
+        occupancy-grid refresh every 16th iteration, which reads mean(occs)).
+
+        Step boundary (sync-free mode, pool sampling): the NEXT iteration's ray batch is drawn and marched between this
+        iteration's backward and its optimiser step -- neither depends on the weights -- so the gradient all-reduce runs
+        underneath ~0.4 ms of independent work and a rank that finishes its backward early does not stall on the slowest
+        rank.  The sequence of sampler draws, and therefore every result, is the same as without the reordering."""
         m = self.model
         if self.flat.data_ptr() != m._flat.data_ptr():
             raise RuntimeError("model parameters were re-allocated after the Trainer was built")
-        totals = torch.zeros((4,), dtype=torch.int32, device=self.dev)     # [marched, kept, sampler candidates, sampler overflow]
+        marched = None
         if rays is None:
-            o, d, target = self.pool.sample(self.n_rays, generator=self.ray_gen, status=totals[2:4])
+            batch, self._prefetched = self._prefetched, None
+            if batch is None:
+                batch = self._draw(march=False)
+            o, d, target, totals, marched = batch["o"], batch["d"], batch["target"], batch["totals"], batch["marched"]
         else:
             o, d, target = rays
+            totals = torch.zeros((4,), dtype=torch.int32, device=self.dev)
         R = o.shape[0]
         sync_free = self.sync_free and R <= self.n_rays
         self._refresh_packed()
         self.update_grids()
-        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d, totals, sync_free=sync_free)
+        ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d, totals, sync_free=sync_free, marched=marched)
         n_kept = ray_idx.numel()                                            # sync-free: the capacity, not the count
         if n_kept > 0:                                                      # run_nerf_acc.py:289
             prec = m._precision_id
@@ -186,14 +224,21 @@ class Trainer:
             if sync_free:
                 kw["n_dev"] = offsets[R:R + 1]
             logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
-            pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world)
+            pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
+                                                             pool=self.pool_bufs if sync_free else None)
             ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
             active = None
             if sync_free:
                 self.grad[-1:].copy_(offsets[R:R + 1])                      # kept count rides behind the gradient
                 active = self.grad[-1:]
-            if self.world > 1:
-                torch.distributed.all_reduce(self.grad, group=self.pg)      # sum of per-rank (1/global-batch)-scaled grads
+            work = None
+            if self.world > 1:                                              # sum of per-rank (1/global-batch)-scaled grads
+                work = torch.distributed.all_reduce(self.grad, group=self.pg, async_op=True)
+            if rays is None and sync_free and self.prefetch:
+                # the occupancy grid is refreshed at the START of iterations that are multiples of 16: march ahead only otherwise
+                self._prefetched = self._draw(march=(self.n_iter + 1) % self.GRID_EVERY != 0)
+            if work is not None:
+                work.wait()
             ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1, active=active)
             self.n_iter_adam += 1
             self.lr = self.lr0 * (self.decay_rate ** (self.n_iter / self.decay_steps))   # run_nerf_acc.py:323-328
@@ -214,7 +259,9 @@ class Trainer:
         grids = [g for g in (self.acc_grid, self.vessel_acc_grid) if g is not None]
         return dict(flat=self.flat.clone(), m=self.exp_avg.clone(), v=self.exp_avg_sq.clone(), n_iter=self.n_iter,
                     n_iter_adam=self.n_iter_adam, lr=self.lr, grids=[(g.occs.clone(), g._binary.clone(), g.occs_mean_host) for g in grids],
-                    gens=(self.ray_gen.get_state(), self.grid_gen.get_state()))
+                    gens=(self.ray_gen.get_state(), self.grid_gen.get_state()), prefetched=self._prefetched,
+                    seed_stream=(self.pool._seed_streams[id(self.ray_gen)].bit_generator.state
+                                 if id(self.ray_gen) in self.pool._seed_streams else None))
 
     def restore(self, snap):
         self.flat.copy_(snap["flat"]); self.exp_avg.copy_(snap["m"]); self.exp_avg_sq.copy_(snap["v"])
@@ -223,6 +270,11 @@ class Trainer:
         for g, (occs, binary, mean) in zip(grids, snap["grids"]):
             g.occs.copy_(occs); g._binary.copy_(binary); g.occs_mean_host = mean
         self.ray_gen.set_state(snap["gens"][0]); self.grid_gen.set_state(snap["gens"][1])
+        self._prefetched = snap.get("prefetched")
+        if snap.get("seed_stream") is not None:
+            rng = np.random.default_rng(0)
+            rng.bit_generator.state = snap["seed_stream"]
+            self.pool._seed_streams[id(self.ray_gen)] = rng
 
     # ------------------------------------------------------------------ checkpoint / resume
     def save_checkpoint(self, filename, extra=None):
@@ -237,8 +289,9 @@ class Trainer:
             exp_avg=self.exp_avg.detach().cpu(), exp_avg_sq=self.exp_avg_sq.detach().cpu(),
             grids=[dict(occs=g.occs.detach().cpu(), binary=g._binary.detach().cpu(), occs_mean=g.occs_mean_host) for g in grids],
             ray_gen=self.ray_gen.get_state().cpu(), grid_gen=self.grid_gen.get_state().cpu(),
-            sampler_seed_stream=(self.pool._seed_streams[id(self.ray_gen)].bit_generator.state
-                                 if id(self.ray_gen) in self.pool._seed_streams else None))
+            sampler_seed_stream=(self._prefetched["pre_state"] if self._prefetched is not None else
+                                 (self.pool._seed_streams[id(self.ray_gen)].bit_generator.state
+                                  if id(self.ray_gen) in self.pool._seed_streams else None)))
         self.model.save(filename, info)
 
     def load_checkpoint(self, filename):
@@ -256,6 +309,7 @@ class Trainer:
         for g, st in zip(grids, res["grids"]):
             g.occs.copy_(st["occs"]); g._binary.copy_(st["binary"]); g.occs_mean_host = st["occs_mean"]
         self.ray_gen.set_state(res["ray_gen"]); self.grid_gen.set_state(res["grid_gen"])
+        self._prefetched = None
         if res.get("sampler_seed_stream") is not None:               # host-side seed stream of the on-device ray sampler
             rng = np.random.default_rng(0)
             rng.bit_generator.state = res["sampler_seed_stream"]
