@@ -45,70 +45,45 @@ def model_def(w, device, precision):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py) from a background thread --
-    the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, without forking a process that
-    polls the driver while the step is being timed.  Falls back to the nvidia-smi loop if NVML cannot be loaded."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py) -- the counters
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints.  The samples are taken inline by the timing loop
+    (every few steps, while the GPU is busy with the steps already enqueued): a background Python thread would contend for the
+    GIL with the thread that launches kernels (5 ms switch interval = visible stalls in a 2.4 ms step), and a polling
+    nvidia-smi process perturbs the driver.  NVML is loaded and exercised once before the timed region."""
 
-    def __init__(self, index, period_s=0.02):
-        self.rows, self.proc, self.index, self.period = [], None, index, period_s
-        self.nvml, self.handle, self.thread, self.stop_flag, self.sm_max = None, None, None, False, None
+    def __init__(self, index):
+        self.rows, self.index, self.nvml, self.handle, self.sm_max, self.bits = [], index, None, None, None, {}
 
-    def start(self):
+    def prepare(self):
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nvml = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
-            self.thread = threading.Thread(target=self._poll, daemon=True)
-            self.thread.start()
-            return
+            import pynvml as n
+            n.nvmlInit()
+            self.handle = n.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            self.bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            self.nvml = n
+            self.sample()
+            self.rows.clear()
         except Exception:
             self.nvml = None
+
+    def sample(self):
+        if self.nvml is None:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            sm = float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            r = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            self.rows.append((sm, [k for k, b in self.bits.items() if r & b]))
         except Exception:
-            self.proc = None
+            pass
 
-    def _poll(self):
-        n = self.nvml
-        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
-                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
-        while not self.stop_flag:
-            try:
-                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
-                r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.rows.append((sm, [k for k, b in bits.items() if r & b]))
-            except Exception:
-                pass
-            time.sleep(self.period)
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.nvml is not None:
-            self.stop_flag = True
-            self.thread.join(timeout=1.0)
-            sm = [r[0] for r in self.rows]
-            reasons = sorted({k for r in self.rows for k in r[1]})
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(sm),
-                    "source": "nvml"}
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm), "source": "nvidia-smi"}
+    def result(self):
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        sm = [r[0] for r in self.rows]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted({k for r in self.rows for k in r[1]}),
+                "samples": len(sm), "source": "nvml, sampled inline while the timed steps execute"}
 
 
 def cpu_oracle_step_time(w, n_rays_cpu, steps=1, seed=0):
@@ -225,27 +200,38 @@ def main():
     torch.cuda.synchronize()
 
     # ---------------- device-resident arm
+    clocks = ClockSampler(local_rank)
+    if not args.no_clocks:
+        clocks.prepare()
     for _ in range(args.warmup):
         tr.step()
     sync_all()
     snap = tr.snapshot()                                               # both arms are timed from this model / grid / optimiser state
     launches0 = int(lib.angio_launch_count())
-    clocks = ClockSampler(local_rank)
-    if not args.no_clocks:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tr.kernel_events = []                                              # (start, end, sample count) per visibility-pass MLP launch
     step_totals = []                                                   # device counters of every step, read after the timed region
     torch.cuda.profiler.start()                                        # ncu --profile-from-start off captures exactly the timed region
     e0.record()
-    for _ in range(args.steps):
+    step_events = []
+    every = max(1, args.steps // 8)
+    for i_step in range(args.steps):
         out = tr.step()
         step_totals.append(out["totals"])
+        if not args.no_clocks and i_step % every == every - 1:
+            clocks.sample()                                            # the GPU is executing the steps enqueued so far
+        if os.environ.get("BENCH_DEBUG"):
+            ev = torch.cuda.Event(enable_timing=True); ev.record(); step_events.append(ev)
     e1.record()
     sync_all()
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if not args.no_clocks else None
+    if step_events:
+        prev, ts = e0, []
+        for ev in step_events:
+            ts.append(prev.elapsed_time(ev)); prev = ev
+        print(f"[rank {rank}] per-step ms: " + " ".join(f"{t:.2f}" for t in ts), file=sys.stderr, flush=True)
+    clk = clocks.result() if not args.no_clocks else None
     launches = int(lib.angio_launch_count()) - launches0
     host_totals = [t.tolist() if isinstance(t, torch.Tensor) else list(t) for t in step_totals]
     if any(len(t) > 3 and t[3] != 0 for t in host_totals):

@@ -244,6 +244,20 @@ ANGIO_API int angio_adam_step(float* params, const float* grads, float* exp_avg,
                     float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
                     const float* active, void* stream);
 
+/* Data-parallel training (one process per GPU): gradient all-reduce fused INTO the optimiser step over NVLink peer memory.
+ * Each rank's gradient lives in a buffer that every peer has mapped (symmetric memory).  After its backward a rank calls
+ * angio_signal_peers (system-scope fence + one tag store into every peer's flag array: peer_flags_host[r] is the DEVICE address
+ * of rank r's flag array [world] as mapped in this process).  angio_adam_step_allreduce waits until my_flags[r] >= tag for all r,
+ * sums the `world` gradient buffers (peer_grads_host[r]: device address of rank r's gradient as mapped here) in rank order --
+ * bit-identical on every rank -- and applies angio_adam_step's update in the same pass.  active_index >= 0 names a gradient
+ * slot whose all-rank sum gates the step (0 = skip), < 0 disables the gate.  Callers alternate two gradient buffers by step
+ * parity.  Replaces the NCCL all_reduce + Adam pair; the pointer arrays are HOST arrays of `world` (<= 16) entries. */
+ANGIO_API int angio_signal_peers(void* const* peer_flags_host, int32_t world, int32_t rank, uint32_t tag, void* stream);
+ANGIO_API int angio_adam_step_allreduce(float* params, const void* const* peer_grads_host, int32_t world,
+                              const uint32_t* my_flags, uint32_t tag, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                              int64_t active_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

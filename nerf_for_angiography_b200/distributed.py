@@ -49,3 +49,38 @@ def gather_concat(local: torch.Tensor, group=None, dst: int = 0):
     if rank != dst:
         return None
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+
+
+class PeerGradients:
+    """Gradient buffers of all ranks mapped into every process (torch symmetric memory over NVLink / NVSwitch) for the fused
+    all-reduce + Adam kernel (angio_adam_step_allreduce).  Layout of each rank's allocation, in 4-byte words:
+    [gradient, even steps (n_alloc) | gradient, odd steps (n_alloc) | flags[world] (uint32 step tags written by the peers)].
+    torch.distributed only does the plumbing (allocation + handle exchange); the data path is our kernel."""
+
+    def __init__(self, n_floats, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise RuntimeError("PeerGradients supports up to 16 ranks (one NVSwitch domain)")
+        self.n = int(n_floats)
+        self.n_alloc = (self.n + 63) // 64 * 64
+        words = 2 * self.n_alloc + 64
+        self.buf = symm.empty(words, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group.group_name if hasattr(group, "group_name") else group)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.grad = [self.buf[k * self.n_alloc:k * self.n_alloc + self.n] for k in range(2)]
+        self.flags = self.buf[2 * self.n_alloc:2 * self.n_alloc + 64].view(torch.int32)
+        import ctypes
+        arr = ctypes.c_void_p * self.world
+        self.peer_grad_ptrs = [arr(*[b + 4 * k * self.n_alloc for b in base]) for k in range(2)]
+        self.peer_flag_ptrs = arr(*[b + 4 * 2 * self.n_alloc for b in base])
+        self.tag = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                       # every rank's buffer is zeroed before anyone signals
+
+    def next_buffer(self):
+        """(gradient buffer of the coming step, its tag).  Tags start at 1; the buffer alternates with the tag's parity."""
+        self.tag += 1
+        return self.grad[self.tag & 1], self.tag

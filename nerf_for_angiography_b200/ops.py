@@ -495,3 +495,19 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.9
     active = _chk(active, torch.float32, "active", 1, allow_none=True)
     _lib.check(lib.angio_adam_step(_p(params), _p(grads), _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1),
                                    float(beta2), float(eps), int(step), float(grad_scale), _p(active), _stream()), "angio_adam_step")
+
+
+def signal_peers(peer, tag):
+    """Publish this rank's step tag to every peer (after its gradient is complete on the current stream)."""
+    _lib.check(_lib.load().angio_signal_peers(peer.peer_flag_ptrs, peer.world, peer.rank, int(tag) & 0xFFFFFFFF, _stream()), "angio_signal_peers")
+
+
+def adam_step_allreduce(params, peer, tag, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0,
+                        active_index=-1):
+    """Adam on the rank-ordered sum of all ranks' gradients, read straight from NVLink peer memory (see angio_b200.h)."""
+    lib = _lib.load()
+    for t, nme in ((params, "params"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _chk(t, torch.float32, nme, 1)
+    _lib.check(lib.angio_adam_step_allreduce(_p(params), peer.peer_grad_ptrs[tag & 1], peer.world, _p(peer.flags), int(tag) & 0xFFFFFFFF,
+                                             _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                             int(step), float(grad_scale), int(active_index), _stream()), "angio_adam_step_allreduce")

@@ -8,6 +8,7 @@ Autograd is not involved: the composite/MSE tail and the MLP backward are explic
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -70,13 +71,25 @@ class Trainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
             self.rank = torch.distributed.get_rank(process_group)
+        # gradients of all ranks in NVLink peer memory -> all-reduce fused into the Adam kernel (ANGIO_P2P=0: NCCL all_reduce)
+        self.peer = None
+        if self.world > 1 and os.environ.get("ANGIO_P2P", "1") != "0" and model._precision_id == ops.PREC_BF16:
+            try:
+                from .distributed import PeerGradients
+                self.peer = PeerGradients(self.flat.numel() + 1, self.dev, process_group)
+            except Exception as e:                                       # no symmetric memory on this system: NCCL path
+                if os.environ.get("ANGIO_P2P") == "1":
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory gradient exchange unavailable ({e!r}); using NCCL all_reduce")
         # rays: every rank draws a different batch; grids: every rank draws the SAME cells/jitter
         self.ray_gen = torch.Generator(device=self.dev).manual_seed(seed + 1000 * self.rank + 1)
         self.grid_gen = torch.Generator(device=self.dev).manual_seed(seed)
         self.last = {}
         self.kernel_events = None     # bench.py: list of (start event, end event, sample count) per visibility-pass MLP launch
         self.sync_free = self._plan_memory(sync_free, memory_fraction)
-        self.prefetch = True          # draw + march the next batch under the gradient all-reduce (sync-free mode)
+        # draw + march the next batch under the gradient all-reduce (sync-free mode); ANGIO_PREFETCH=0 keeps the plain order
+        self.prefetch = os.environ.get("ANGIO_PREFETCH", "1") != "0"
         self._prefetched = None
         self._march_calls = 0
         # visibility pass with early ray termination (bf16 path): number of leading samples per ray evaluated before the rays
@@ -226,20 +239,29 @@ class Trainer:
             logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
             pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
                                                              pool=self.pool_bufs if sync_free else None)
+            use_peer = self.peer is not None and sync_free
+            if use_peer:
+                self.grad, tag = self.peer.next_buffer()                    # this step's gradient lives in NVLink peer memory
             ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
             active = None
             if sync_free:
                 self.grad[-1:].copy_(offsets[R:R + 1])                      # kept count rides behind the gradient
                 active = self.grad[-1:]
             work = None
-            if self.world > 1:                                              # sum of per-rank (1/global-batch)-scaled grads
+            if use_peer:
+                ops.signal_peers(self.peer, tag)                            # gradient complete -> tag to every peer
+            elif self.world > 1:                                            # sum of per-rank (1/global-batch)-scaled grads
                 work = torch.distributed.all_reduce(self.grad, group=self.pg, async_op=True)
             if rays is None and sync_free and self.prefetch:
                 # the occupancy grid is refreshed at the START of iterations that are multiples of 16: march ahead only otherwise
                 self._prefetched = self._draw(march=(self.n_iter + 1) % self.GRID_EVERY != 0)
             if work is not None:
                 work.wait()
-            ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1, active=active)
+            if use_peer:                                                    # waits for all tags, sums over NVLink, Adam -- one kernel
+                ops.adam_step_allreduce(self.flat, self.peer, tag, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1,
+                                        active_index=self.flat.numel())
+            else:
+                ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1, active=active)
             self.n_iter_adam += 1
             self.lr = self.lr0 * (self.decay_rate ** (self.n_iter / self.decay_steps))   # run_nerf_acc.py:323-328
             loss = loss_sum / R

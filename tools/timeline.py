@@ -26,7 +26,11 @@ def main():
     ap.add_argument("--precision", default="bf16")
     args = ap.parse_args()
     w = bench.WORKLOADS[args.workload]
-    dev = torch.device("cuda", 0)
+    rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:                                    # under torchrun: every rank trains, rank 0 prints its own timeline
+        torch.distributed.init_process_group("nccl", device_id=dev)
     pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], kind="ct", volume_res=w["vol"], device=dev)
     model = A.CPPN(bench.model_def(w, dev, args.precision)).to(dev)
     tr = Trainer(model, pool, info["near"], info["far"], n_rays=w["rays"])
@@ -38,6 +42,11 @@ def main():
         for _ in range(args.steps):
             tr.step()
         torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     if not evs:
