@@ -286,6 +286,12 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback",
                             "avg_launch_ms": float(np.mean([t for _, t in big])), "samples_per_launch": float(np.mean([n for n, _ in big])),
                             "launches_timed": len(big)}
+                try:   # DRAM bytes of this kernel from the committed `ncu --set full` capture, scaled to this run's samples per launch
+                    tr_ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["mlp_fwd_tc_kernel<ALPHA>"]
+                    roofline["traffic"] = tr_ncu["dram_bytes"] / tr_ncu["samples"] * roofline["samples_per_launch"]
+                    roofline["traffic_source"] = tr_ncu["source"]
+                except Exception:
+                    pass
         cpu = None
         if not args.no_cpu_baseline:
             n_cpu = 1024 if args.workload != "tiny" else 256
