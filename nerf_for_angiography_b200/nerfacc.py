@@ -153,10 +153,11 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
     if (alpha_thre > 0.0 or early_stop_eps > 0.0) and have_fn and ray_idx.numel() > 0:
         if radiance_field is not None and _is_fused_model(radiance_field):
             m = radiance_field
-            if m._precision_id == ops.PREC_BF16 and early_stop_eps > 0.0:
+            if early_stop_eps > 0.0:
                 # two-phase visibility pass with early ray termination: same kept samples as evaluating every sample
                 m._ensure_flat()
-                alphas, _ = ops.alphas_two_phase(m._desc, m._flat, m._packed_weights(), m._precision_id, rays_o, rays_d, ray_idx, t0, t1,
+                packed = m._packed_weights() if m._precision_id == ops.PREC_BF16 else None
+                alphas, _ = ops.alphas_two_phase(m._desc, m._flat, packed, m._precision_id, rays_o, rays_d, ray_idx, t0, t1,
                                                  offsets, early_stop_eps)
             else:
                 alphas = m.query(ops.OUT_ALPHA, rays_o=rays_o, rays_d=rays_d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)

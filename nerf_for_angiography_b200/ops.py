@@ -268,7 +268,16 @@ def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t
             if timing is not None:                         # bench.py: CUDA events around each MLP launch + its device sample count
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            mlp_forward(desc, params, packed, OUT_ALPHA, precision, out=alphas, sample_idx=ids, n_dev=seg[R:R + 1], pool=pool, **kw)
+            if precision == PREC_BF16:
+                mlp_forward(desc, params, packed, OUT_ALPHA, precision, out=alphas, sample_idx=ids, n_dev=seg[R:R + 1], pool=pool, **kw)
+            else:
+                # fp32 check path (any MLP shape): the subset is gathered into exact-size arrays (one host read of its length)
+                m = int(seg[R].item())
+                if m > 0:
+                    sel = ids[:m].long()
+                    sub = mlp_forward(desc, params, packed, OUT_ALPHA, precision, rays_o=rays_o, rays_d=rays_d,
+                                      ray_idx=ray_idx[sel].contiguous(), t_starts=t_starts[sel].contiguous(), t_ends=t_ends[sel].contiguous())
+                    alphas[sel] = sub
             if timing is not None:
                 ev1.record()
                 timing.append((ev0, ev1, evaluated[phase:phase + 1]))

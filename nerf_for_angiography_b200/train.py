@@ -171,7 +171,7 @@ class Trainer:
         ray_idx, t0, t1, offsets = marched if marched is not None else self._march(o, d, totals, pooled=sync_free)
         n_pre = ray_idx.numel()
         if n_pre > 0:
-            if bf16 and self.early_termination:
+            if self.early_termination:
                 # same kept set as evaluating every sample; only samples that can still be visible reach the MLP
                 alphas, _ = ops.alphas_two_phase(self.model._desc, self.flat, self.packed, self.model._precision_id, o, d, ray_idx,
                                                  t0, t1, offsets, self.early_stop_eps, k0=self.early_termination, timing=self.kernel_events,
