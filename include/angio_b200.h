@@ -244,6 +244,17 @@ ANGIO_API int angio_adam_step(float* params, const float* grads, float* exp_avg,
                     float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
                     const float* active, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Ground-truth projector (synthetic data generation).   Replaces ray_tracing (phantomdata/helpers.py:192-224): trilinear
+ * lookups (0 outside the grid, like scipy's RegularGridInterpolator(bounds_error=False, fill_value=0)) of volume[nx,ny,nz]
+ * (x-major, spanning bounds_host = min xyz, max xyz) at o + d * depths[k]; ct_mode 1: exp(-sum mu_k * dist_k * |d|) with
+ * dist = diff(depths) and the reference's 1e10 tail; ct_mode 0 ('sdf'): exp(-sum mu_k).  depths: [n_depths] DEVICE floats
+ * shared by all rays.  out: [n_rays].
+ */
+ANGIO_API int angio_project_volume(const float* volume, int32_t nx, int32_t ny, int32_t nz, const float* bounds_host,
+                         const float* rays_o, const float* rays_d, int64_t n_rays, const float* depths,
+                         int32_t n_depths, int32_t ct_mode, float* out, void* stream);
+
 /* Data-parallel training (one process per GPU): gradient all-reduce fused INTO the optimiser step over NVLink peer memory.
  * Each rank's gradient lives in a buffer that every peer has mapped (symmetric memory).  After its backward a rank calls
  * angio_signal_peers (system-scope fence + one tag store into every peer's flag array: peer_flags_host[r] is the DEVICE address

@@ -60,6 +60,7 @@ PROTOTYPES = {
     "angio_grid_cell_points": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr]),
     "angio_grid_ema_update": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_i64, c_f32, c_ptr, c_i64, c_ptr]),
     "angio_grid_threshold": (c_i32, [c_ptr, c_i64, c_f32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "angio_project_volume": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     "angio_signal_peers": (c_i32, [c_ptr, c_i32, c_i32, ctypes.c_uint32, c_ptr]),
     "angio_adam_step_allreduce": (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, ctypes.c_uint32, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32,
                                           c_f32, c_i64, c_ptr]),

@@ -1,0 +1,77 @@
+// projector.cu -- ground-truth cone-beam projector of an attenuation volume (synthetic data generation).
+// Replaces ray_tracing (/root/reference/phantomdata/helpers.py:192-224), which evaluates a scipy RegularGridInterpolator
+// (trilinear, 0 outside the grid) on the CPU in 100 x 100-pixel tiles: query points o + d * depth_k for one shared vector of
+// depths, dists = diff(depths) with the reference's 1e10 tail, weights exp(-mu * dist * |d|) ('ct', :208-211) or exp(-mu)
+// ('sdf', :213-215), pixel = product of the weights.
+// One thread per ray; the product of exponentials is accumulated as exp(-sum) in fp32.  The volume (256^3 fp32 = 64 MB) is
+// read through the read-only path and mostly stays in the 126 MB L2; 8 loads per sample, 4 B/ray written.
+#include "common.cuh"
+
+namespace {
+
+struct VolumeDesc {
+  int nx, ny, nz;
+  float lo[3], scale[3];   // grid coordinate = (p - lo) * scale, scale = (n - 1) / (hi - lo)
+};
+
+__device__ __forceinline__ float trilinear(const float* __restrict__ vol, const VolumeDesc& v, float px, float py, float pz) {
+  const float gx = (px - v.lo[0]) * v.scale[0], gy = (py - v.lo[1]) * v.scale[1], gz = (pz - v.lo[2]) * v.scale[2];
+  if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx <= (float)(v.nx - 1) && gy <= (float)(v.ny - 1) && gz <= (float)(v.nz - 1)))
+    return 0.0f;                                               // bounds_error=False, fill_value=0
+  int ix = min((int)gx, v.nx - 2), iy = min((int)gy, v.ny - 2), iz = min((int)gz, v.nz - 2);
+  ix = max(ix, 0); iy = max(iy, 0); iz = max(iz, 0);
+  const float fx = gx - (float)ix, fy = gy - (float)iy, fz = gz - (float)iz;
+  const int64_t sx = (int64_t)v.ny * v.nz, sy = v.nz;
+  const float* b = vol + ix * sx + iy * sy + iz;
+  const float c000 = __ldg(b), c001 = __ldg(b + 1), c010 = __ldg(b + sy), c011 = __ldg(b + sy + 1);
+  const float c100 = __ldg(b + sx), c101 = __ldg(b + sx + 1), c110 = __ldg(b + sx + sy), c111 = __ldg(b + sx + sy + 1);
+  const float c00 = c000 + (c001 - c000) * fz, c01 = c010 + (c011 - c010) * fz;
+  const float c10 = c100 + (c101 - c100) * fz, c11 = c110 + (c111 - c110) * fz;
+  const float c0 = c00 + (c01 - c00) * fy, c1 = c10 + (c11 - c10) * fy;
+  return c0 + (c1 - c0) * fx;
+}
+
+__global__ void __launch_bounds__(128) project_kernel(const float* __restrict__ vol, VolumeDesc v, const float* __restrict__ rays_o,
+                                                      const float* __restrict__ rays_d, int64_t n_rays, const float* __restrict__ depths,
+                                                      int n_depths, int ct_mode, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rays) return;
+  const float ox = rays_o[i * 3], oy = rays_o[i * 3 + 1], oz = rays_o[i * 3 + 2];
+  const float dx = rays_d[i * 3], dy = rays_d[i * 3 + 1], dz = rays_d[i * 3 + 2];
+  const float dnorm = ct_mode ? sqrtf(dx * dx + dy * dy + dz * dz) : 1.0f;
+  float tau = 0.0f;
+  float t = depths[0];
+  for (int k = 0; k < n_depths; ++k) {
+    const float t_next = (k + 1 < n_depths) ? depths[k + 1] : 0.0f;
+    const float mu = trilinear(vol, v, ox + dx * t, oy + dy * t, oz + dz * t);
+    if (ct_mode) {
+      const float dist = (k + 1 < n_depths) ? (t_next - t) : 1e10f;          // the reference's 1e10 tail (helpers.py:202)
+      if (mu != 0.0f) tau += mu * (dist * dnorm);
+    } else {
+      tau += mu;
+    }
+    t = t_next;
+  }
+  out[i] = __expf(-tau);
+}
+
+}  // namespace
+
+extern "C" int angio_project_volume(const float* volume, int32_t nx, int32_t ny, int32_t nz, const float* bounds_host, const float* rays_o,
+                                    const float* rays_d, int64_t n_rays, const float* depths, int32_t n_depths, int32_t ct_mode, float* out,
+                                    void* stream) {
+  ANGIO_REQUIRE(volume && bounds_host && rays_o && rays_d && depths && out, "angio_project_volume: null pointer");
+  ANGIO_REQUIRE(nx >= 2 && ny >= 2 && nz >= 2 && n_rays >= 0 && n_depths >= 1, "angio_project_volume: bad sizes");
+  if (n_rays == 0) return 0;
+  VolumeDesc v;
+  v.nx = nx; v.ny = ny; v.nz = nz;
+  const int n[3] = {nx, ny, nz};
+  for (int k = 0; k < 3; ++k) {
+    ANGIO_REQUIRE(bounds_host[3 + k] > bounds_host[k], "angio_project_volume: empty bounds");
+    v.lo[k] = bounds_host[k];
+    v.scale[k] = (float)(n[k] - 1) / (bounds_host[3 + k] - bounds_host[k]);
+  }
+  angio::note_launch(); project_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(volume, v, rays_o, rays_d, n_rays, depths,
+                                                                                                       n_depths, ct_mode, out);
+  return angio::finish_launch("angio_project_volume");
+}

@@ -4,8 +4,8 @@ device-resident ray pool that replaces the reference's CSV/pandas DataFrame of p
 The reference's datasets cannot be shared (README.md:18) and its ``load_data`` is missing
 (nerf/run_nerf_acc.py:82), so the benchmark / test inputs are generated here following the reference's
 phantom pipeline (/root/reference/phantomdata/cttoray.py:189-262, helpers.py:17-18,192-224):
-volume -> trilinear interpolation along each ray -> Beer-Lambert product.  This is input preparation
-(plain torch ops on the GPU), not the hot path.
+volume -> trilinear interpolation along each ray -> Beer-Lambert product (a CUDA kernel of its own:
+csrc/projector.cu).  This is input preparation, not the hot path.
 """
 import math
 
@@ -78,27 +78,14 @@ def make_volume(resolution=256, half_extent=100.0, kind="sdf", device="cuda", se
 
 
 @torch.no_grad()
-def project(volume, rays_o, rays_d, near, far, n_samples=300, half_extent=100.0, kind="ct", chunk=1 << 18):
-    """Ground-truth projector (/root/reference/phantomdata/helpers.py:192-224): trilinear lookups at evenly spaced
-    depths, I = prod exp(-mu * dt * |d|) ('ct', :208-211) or prod exp(-mu) ('sdf', :213-215)."""
-    n = rays_o.shape[0]
-    out = torch.empty(n, dtype=torch.float32, device=rays_o.device)
-    t = torch.linspace(near, far, n_samples, device=rays_o.device)
-    dt = (far - near) / (n_samples - 1)
-    vol5 = volume[None, None]                                    # [1,1,X,Y,Z]
-    for i0 in range(0, n, chunk):
-        o = rays_o[i0:i0 + chunk]
-        d = rays_d[i0:i0 + chunk]
-        pts = o[:, None, :] + d[:, None, :] * t[None, :, None]  # [m, S, 3]
-        g = (pts / half_extent).flip(-1)                         # grid_sample wants (z, y, x) order for [X,Y,Z] volumes
-        mu = torch.nn.functional.grid_sample(vol5, g[None, :, :, None, :], mode="bilinear", padding_mode="zeros",
-                                             align_corners=True)[0, 0, :, :, 0]
-        if kind == "ct":
-            tau = (mu.sum(dim=1) * dt) * d.norm(dim=-1)
-        else:
-            tau = mu.sum(dim=1)
-        out[i0:i0 + chunk] = torch.exp(-tau)
-    return out
+def project(volume, rays_o, rays_d, near, far, n_samples=300, half_extent=100.0, kind="ct"):
+    """Ground-truth projector (/root/reference/phantomdata/helpers.py:192-224) on the GPU (angio_project_volume): trilinear
+    lookups at evenly spaced depths (the reference's non-stratified depth values), I = prod exp(-mu * dist * |d|) ('ct',
+    :208-211) or prod exp(-mu) ('sdf', :213-215).  The volume spans [-half_extent, half_extent]^3."""
+    depths = torch.linspace(float(near), float(far), int(n_samples), device=rays_o.device, dtype=torch.float32)
+    h = float(half_extent)
+    return ops.project_volume(volume.contiguous().float(), np.array([-h, -h, -h, h, h, h], np.float32), rays_o.contiguous().float(),
+                              rays_d.contiguous().float(), depths, kind)
 
 
 # ------------------------------------------------------------------------------------------------ ray pool

@@ -520,3 +520,20 @@ def adam_step_allreduce(params, peer, tag, exp_avg, exp_avg_sq, lr, step, beta1=
     _lib.check(lib.angio_adam_step_allreduce(_p(params), peer.peer_grad_ptrs[tag & 1], peer.world, _p(peer.flags), int(tag) & 0xFFFFFFFF,
                                              _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                              int(step), float(grad_scale), int(active_index), _stream()), "angio_adam_step_allreduce")
+
+
+def project_volume(volume, bounds, rays_o, rays_d, depths, kind="ct"):
+    """Ground-truth Beer-Lambert projection of an attenuation volume [X,Y,Z] along rays (phantomdata/helpers.py:192-224)."""
+    lib = _lib.load()
+    volume = _chk(volume, torch.float32, "volume", 3)
+    rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
+    rays_d = _chk(rays_d, torch.float32, "ray_directions", 2)
+    depths = _chk(depths, torch.float32, "depths", 1)
+    if kind not in ("ct", "sdf"):
+        raise ValueError("kind must be 'ct' or 'sdf'")
+    b = _host6(bounds, "bounds")
+    n = rays_o.shape[0]
+    out = torch.empty((n,), dtype=torch.float32, device=volume.device)
+    _lib.check(lib.angio_project_volume(_p(volume), volume.shape[0], volume.shape[1], volume.shape[2], b.ctypes.data, _p(rays_o), _p(rays_d), n,
+                                        _p(depths), depths.numel(), 1 if kind == "ct" else 0, _p(out), _stream()), "angio_project_volume")
+    return out

@@ -88,6 +88,11 @@ class Trainer:
         self.last = {}
         self.kernel_events = None     # bench.py: list of (start event, end event, sample count) per visibility-pass MLP launch
         self.sync_free = self._plan_memory(sync_free, memory_fraction)
+        if self.world > 1:
+            # the peer-memory gradient exchange needs every rank on the same path: sync-free only if ALL ranks can afford it
+            flag = torch.tensor([1 if self.sync_free else 0], dtype=torch.int32, device=self.dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN, group=process_group)
+            self.sync_free = bool(flag.item())
         # draw + march the next batch under the gradient all-reduce (sync-free mode); ANGIO_PREFETCH=0 keeps the plain order
         self.prefetch = os.environ.get("ANGIO_PREFETCH", "1") != "0"
         self._prefetched = None
