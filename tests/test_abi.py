@@ -50,6 +50,17 @@ def test_argument_validation_without_gpu():
     assert rc == _lib.ERR_INVALID_ARG
     with pytest.raises(RuntimeError):
         _lib.check(rc, "angio_raygen")
+    # entry points added for the sync-free / multi-GPU path reject bad arguments the same way (no GPU work is attempted)
+    assert lib.angio_sample_rays(None, 100, 200, 1, 1.0, 300, None, None, None, 0, None) == _lib.ERR_INVALID_ARG       # n > n_pool
+    assert lib.angio_sample_rays_workspace_bytes(0, 10) == _lib.ERR_INVALID_ARG
+    assert lib.angio_sample_rays_workspace_bytes(1000, 100) > 1000 * 12
+    assert lib.angio_march_runs_bytes(65536) == (3 * 8 + 1) * 65536 * 4
+    assert lib.angio_ray_segment_counts(None, 10, 0, 32, None, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.angio_visibility_head(None, None, 10, 0, 0.01, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.angio_project_volume(None, 8, 8, 8, None, None, None, 10, None, 4, 1, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.angio_signal_peers(None, 2, 0, 1, None) == _lib.ERR_INVALID_ARG
+    assert lib.angio_adam_step_allreduce(None, None, 2, None, 1, None, None, 10, 1e-4, 0.9, 0.999, 1e-8, 1, 1.0, -1, None) == _lib.ERR_INVALID_ARG
+    assert b"angio_adam_step_allreduce" in lib.angio_last_error_string()
 
 
 def test_python_surface_fails_loudly_on_cpu_tensors():

@@ -345,6 +345,26 @@ def test_weighted_sampling_without_replacement(A):
     assert ids.unique().numel() == 1000
 
 
+def test_sampler_edge_cases(A):
+    """n = 1, a pool where almost every weight is zero (only positive-weight rays may be drawn), and n = every positive ray."""
+    from nerf_for_angiography_b200.data import RayPool
+    V, H, W = 2, 64, 64
+    w = torch.zeros(V, H, W, device="cuda")
+    pos = torch.randperm(V * H * W, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))[:300]
+    w.view(-1)[pos] = torch.rand(300, device="cuda") + 0.1
+    pool = RayPool(torch.eye(4, dtype=torch.float64, device="cuda").repeat(V, 1, 1), torch.rand(V, H, W, device="cuda"), 100.0, w)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    one = pool.sample_ids(1, generator=g)
+    assert one.numel() == 1 and float(w.view(-1)[one]) > 0 and pool.last_status.tolist()[1] == 0
+    some = pool.sample_ids(100, generator=g)
+    assert some.unique().numel() == 100 and bool((w.view(-1)[some] > 0).all())
+    allpos = pool.sample_ids(300, generator=g)
+    assert allpos.sort().values.equal(pos.sort().values) and pool.last_status.tolist()[1] == 0
+    # asking for more rays than have positive weight cannot be satisfied: the status flag says so instead of returning garbage silently
+    pool.sample_ids(301, generator=g)
+    assert pool.last_status.tolist()[1] == 1
+
+
 def test_sampler_is_reproducible_and_shuffled(A):
     """Same seed -> the same ids in the same order (the candidate pass appends with atomics, the select/shuffle pass must
     erase that order); the order is a uniform shuffle (no correlation between position and ray id or weight)."""

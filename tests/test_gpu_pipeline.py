@@ -294,6 +294,38 @@ def test_two_phase_visibility_equals_full_evaluation(A, bias_shift):
         assert ev[0] + ev[1] == ri.numel()                    # thin field: nothing terminates, every sample is evaluated
 
 
+def test_two_phase_visibility_ragged_rays(A):
+    """Rays with fewer than 32 samples, exactly 32, and none at all (single occupied slab): the index lists stay consistent and
+    the result still equals the full evaluation."""
+    res = 32
+    binary = np.zeros((res,) * 3, bool)
+    binary[14:18, :, :] = True                                          # a 25-unit slab: 0 .. ~40 samples per ray
+    roi = np.array([-100, -100, -100, 100, 100, 100], np.float32)
+    gg = A.OccupancyGrid(torch.tensor(roi), res, A.ContractionType.AABB).cuda()
+    gg._binary = torch.from_numpy(binary).cuda()
+    os_, ds_ = [], []
+    for th, ph in ((0.0, 0.0), (70.0, 20.0), (135.0, 135.0)):
+        o, d, _ = ogeo.get_ray_values(th, ph, 0.0, [0, 0, 1500.0], 32, 32, 7.5 * 32)
+        os_.append(o.reshape(-1, 3)); ds_.append(d.reshape(-1, 3))
+    ro = torch.from_numpy(np.concatenate(os_).astype(np.float32)).cuda()
+    rd = torch.from_numpy(np.concatenate(ds_).astype(np.float32)).cuda()
+    p = ocppn.init_params(4, 128, "fourier", 5, 0.05, seed=3)
+    p["output_linear.0.bias"] = p["output_linear.0.bias"] - 2.0
+    model = A.CPPN(_model_def(4, 128, "fourier", "bf16"))
+    model.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    model = model.to("cuda"); model._ensure_flat()
+    packed = A.ops.mlp_pack(model._desc, model._flat)
+    ri, t0, t1, off = A.ops.march(ro, rd, roi, roi, res, gg._binary_u8(), 1400.0, 1600.0, 200.0 / 300)
+    cnt = (off[1:] - off[:-1])
+    assert int(cnt.min()) == 0 and int((cnt < 32).sum()) > 100 and int((cnt > 32).sum()) > 100
+    kw = dict(rays_o=ro, rays_d=rd, ray_idx=ri, t_starts=t0, t_ends=t1)
+    full = A.ops.mlp_forward(model._desc, model._flat, packed, A.ops.OUT_ALPHA, A.ops.PREC_BF16, **kw)
+    two, ev = A.ops.alphas_two_phase(model._desc, model._flat, packed, A.ops.PREC_BF16, ro, rd, ri, t0, t1, off, 1e-2, k0=32)
+    assert ev.tolist()[0] == int(torch.clamp(cnt, max=32).sum())
+    for x, y in zip(A.ops.visibility_compact(full, off, t0, t1, 1e-2, 1e-4), A.ops.visibility_compact(two, off, t0, t1, 1e-2, 1e-4)):
+        assert x.equal(y)
+
+
 def test_checkpoint_resume_is_exact(A, tmp_path):
     """save_checkpoint -> fresh Trainer.load_checkpoint -> the continued run is bit-identical to the uninterrupted one; the
     file has the reference's .pth layout (model/CPPN.py:261-276) and its state_dict loads into a new CPPN."""
