@@ -156,8 +156,9 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
             if early_stop_eps > 0.0:
                 # two-phase visibility pass with early ray termination: same kept samples as evaluating every sample
                 m._ensure_flat()
-                packed = m._packed_weights() if m._precision_id == ops.PREC_BF16 else None
-                alphas, _ = ops.alphas_two_phase(m._desc, m._flat, packed, m._precision_id, rays_o, rays_d, ray_idx, t0, t1,
+                kp = m._kernel_params()
+                packed = m._packed_weights(kp) if m._precision_id == ops.PREC_BF16 else None
+                alphas, _ = ops.alphas_two_phase(m._desc, kp, packed, m._precision_id, rays_o, rays_d, ray_idx, t0, t1,
                                                  offsets, early_stop_eps)
             else:
                 alphas = m.query(ops.OUT_ALPHA, rays_o=rays_o, rays_d=rays_d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)

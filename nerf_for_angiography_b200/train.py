@@ -57,6 +57,7 @@ class Trainer:
         self.vessel_acc_grid = OccupancyGrid(self.scene_aabb, grid_resolution, ContractionType.AABB).to(self.dev) if vessel_grid else None
         model._ensure_flat()
         self.flat = model._flat
+        self.kflat = self.flat
         # one extra slot behind the gradient carries the kept-sample count through the all-reduce (Adam skips on 0)
         self.grad = torch.zeros(self.flat.numel() + 1, dtype=torch.float32, device=self.dev)
         self.exp_avg = torch.zeros_like(self.flat)
@@ -125,7 +126,7 @@ class Trainer:
 
     # ------------------------------------------------------------------ pieces
     def _occ_eval(self, x):
-        return ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x)
+        return ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x)
 
     def update_grids(self):
         """acc_update_n_step for both grids (run_nerf_acc.py:285-286)."""
@@ -178,14 +179,14 @@ class Trainer:
         if n_pre > 0:
             if self.early_termination:
                 # same kept set as evaluating every sample; only samples that can still be visible reach the MLP
-                alphas, _ = ops.alphas_two_phase(self.model._desc, self.flat, self.packed, self.model._precision_id, o, d, ray_idx,
+                alphas, _ = ops.alphas_two_phase(self.model._desc, self.kflat, self.packed, self.model._precision_id, o, d, ray_idx,
                                                  t0, t1, offsets, self.early_stop_eps, k0=self.early_termination, timing=self.kernel_events,
                                                  pool=self.pool_bufs if sync_free else None)
             else:
                 if self.kernel_events is not None:
                     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                alphas = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
+                alphas = ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_ALPHA, self.model._precision_id,
                                          rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1,
                                          n_dev=offsets[R:R + 1] if bf16 else None)
                 if self.kernel_events is not None:
@@ -205,8 +206,11 @@ class Trainer:
         return ray_idx, t0, t1, offsets, n_pre
 
     def _refresh_packed(self):
+        """Parameters as the kernels see them this step (the master buffer itself unless the model folds a BARF mask into its
+        first layer) and, on the bf16 path, their packed bf16 image."""
+        self.kflat = self.model._kernel_params()
         if self.model._precision_id == ops.PREC_BF16:
-            self.packed = ops.mlp_pack(self.model._desc, self.flat, self.packed)
+            self.packed = ops.mlp_pack(self.model._desc, self.kflat, self.packed)
 
     # ------------------------------------------------------------------ one reference iteration
     def step(self, rays=None):
@@ -241,13 +245,14 @@ class Trainer:
             kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
             if sync_free:
                 kw["n_dev"] = offsets[R:R + 1]
-            logits, saved = ops.mlp_forward(m._desc, self.flat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
+            logits, saved = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
             pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
                                                              pool=self.pool_bufs if sync_free else None)
             use_peer = self.peer is not None and sync_free
             if use_peer:
                 self.grad, tag = self.peer.next_buffer()                    # this step's gradient lives in NVLink peer memory
-            ops.mlp_backward(m._desc, self.flat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
+            ops.mlp_backward(m._desc, self.kflat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
+            m._map_grad_(self.grad)                                         # BARF: chain rule through the folded mask (no-op otherwise)
             active = None
             if sync_free:
                 self.grad[-1:].copy_(offsets[R:R + 1])                      # kept count rides behind the gradient
@@ -351,7 +356,7 @@ class Trainer:
         ray_idx, t0, t1, offsets, _ = self.march_and_filter(o, d, sync_free=False)    # exact-size arrays for the eval path
         if ray_idx.numel() == 0:
             return torch.ones_like(target), target
-        logits = ops.mlp_forward(self.model._desc, self.flat, self.packed, ops.OUT_LOGIT, self.model._precision_id,
+        logits = ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_LOGIT, self.model._precision_id,
                                  rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
         zero = None
         if binary_thresh is not None:

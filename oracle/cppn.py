@@ -3,7 +3,7 @@
 Functional fp32 (or fp64) torch-CPU restatement of the reference MLP
 (/root/reference/model/CPPN.py:166-222, construction :96-131) restricted to the
 configuration the driver uses: relu, no skip, no view directions, pos_enc in
-{'none', 'fourier'}.  Parameters are passed as a dict with the reference's own
+{'none', 'fourier', 'barf'}.  Parameters are passed as a dict with the reference's own
 state-dict key names (``early_pts_layers.{0,2,..}.{weight,bias}``, ``output_linear.0.*``,
 ``fourier_coefficients``), so a reference checkpoint's ``['model']`` dict works as is.
 Pinned against the reference class by tests/golden/make_golden.py.
@@ -23,13 +23,39 @@ def fourier_features(x, coeff, basis):
     return torch.cat([x, torch.sin(a), torch.cos(a)], dim=-1)
 
 
+def barf_weights(barf_alpha, basis, n_channels=3):
+    """CPPN.barf_coefficients, /root/reference/model/CPPN.py:242-259, quirks included (3.1415, alpha - k + 1)."""
+    k_values = torch.repeat_interleave(torch.arange(0., basis), n_channels)
+    w = []
+    for k in k_values:
+        barf_k = barf_alpha - (k + 1)
+        if barf_k < 0:
+            w.append(0)
+        elif barf_k < 1:
+            w.append((1 - torch.cos((barf_alpha - k + 1) * 3.1415)) / 2)
+        else:
+            w.append(1)
+    return torch.Tensor(w)
+
+
+def barf_features(x, weights, basis):
+    """CPPN.pos_enc + barf_pos_enc, /root/reference/model/CPPN.py:207-234: freq = float32(2^k * pi), one multiply."""
+    k_values = torch.repeat_interleave(torch.arange(0., basis), x.shape[-1])
+    freq = torch.Tensor(2 ** k_values * np.pi)
+    v = torch.cat(basis * [x], dim=-1)
+    a = freq * v
+    return torch.cat([x, weights * torch.sin(a), weights * torch.cos(a)], dim=-1)
+
+
 def cppn_forward(params, x, pos_enc="none", basis=5):
     """x[S,3] -> raw logit [S,1].  /root/reference/model/CPPN.py:166-205."""
     h = x
     if pos_enc == "fourier" and basis > 0:
         h = fourier_features(x, params["fourier_coefficients"], basis)
+    elif pos_enc == "barf" and basis > 0:
+        h = barf_features(x, params["barf_weights"], basis)
     elif pos_enc != "none":
-        raise ValueError("oracle restates pos_enc in {'none','fourier'} only")
+        raise ValueError("oracle restates pos_enc in {'none','fourier','barf'} only")
     for i in range(n_hidden_linears(params)):
         w = params[f"early_pts_layers.{2 * i}.weight"]
         b = params[f"early_pts_layers.{2 * i}.bias"]

@@ -87,6 +87,31 @@ def main():
                 out["grad:" + k] = v.grad.numpy()
         np.savez_compressed(os.path.join(OUT, f"cppn_{tag}.npz"), **out)
 
+    # ---------------------------------------------------------------- CPPN with BARF encoding (f4): forward + grads at several alphas
+    torch.manual_seed(0)
+    params = {'num_early_layers': 4, 'num_late_layers': 0, 'num_filters': 128, 'num_input_channels': 3,
+              'num_output_channels': 1, 'num_input_channels_views': 0, 'use_bias': True, 'pos_enc': 'barf',
+              'pos_enc_basis': 5, 'act_func': 'relu', 'fourier_sigma': 5, 'num_img': 1, 'device': dev}
+    model = CPPN(params)
+    x = (torch.rand(160, 3) * 2 - 1) * 1.5           # BARF frequencies reach 16 pi: keep |x| small so fp32 phases stay meaningful
+    out = {"x": x.numpy(), "alphas": np.array([0.0, 0.6, 1.0, 2.35, 3.999, 5.0, 7.0])}
+    for k, v in model.state_dict().items():
+        if k != "barf_weights":
+            out["sd:" + k] = v.detach().numpy()
+    for ai, a in enumerate(out["alphas"]):
+        model.update_barf_alpha(float(a), 'pts')
+        model.zero_grad()
+        y = model(x)
+        g = torch.randn(y.shape, generator=torch.Generator().manual_seed(100 + ai))
+        (y * g).sum().backward()
+        out[f"a{ai}_weights"] = model.barf_weights.detach().numpy()
+        out[f"a{ai}_y"] = y.detach().numpy()
+        out[f"a{ai}_gout"] = g.numpy()
+        for k, v in model.named_parameters():
+            if v.grad is not None and k != "barf_weights":
+                out[f"a{ai}_grad:" + k] = v.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "cppn_barf_4x128.npz"), **out)
+
     # ---------------------------------------------------------------- composite (a10) + midpoints (a7)
     torch.manual_seed(1)
     n_rays = 37

@@ -40,6 +40,24 @@ def test_cppn_forward_and_grads(golden_dir, tag, pos_enc):
             assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6), k
 
 
+def test_cppn_barf_forward_and_grads(golden_dir):
+    """BARF encoding (f4): mask weights with the reference's quirks, forward and gradients at seven alphas, against the
+    reference's own CPPN(pos_enc='barf')."""
+    g = _load(golden_dir, "cppn_barf_4x128.npz")
+    x = torch.from_numpy(g["x"])
+    for ai, a in enumerate(g["alphas"]):
+        w = cppn.barf_weights(float(a), 5)
+        assert torch.equal(w, torch.from_numpy(g[f"a{ai}_weights"])), a
+        params = {k[3:]: torch.from_numpy(g[k]).clone().requires_grad_(True) for k in g.files if k.startswith("sd:")}
+        params["barf_weights"] = w
+        y = cppn.cppn_forward(params, x, "barf", 5)
+        assert torch.equal(y.detach(), torch.from_numpy(g[f"a{ai}_y"]))
+        (y * torch.from_numpy(g[f"a{ai}_gout"])).sum().backward()
+        for k in g.files:
+            if k.startswith(f"a{ai}_grad:"):
+                assert torch.allclose(params[k.split(":", 1)[1]].grad, torch.from_numpy(g[k]), rtol=1e-5, atol=1e-6), (a, k)
+
+
 def test_composite_and_midpoints(golden_dir):
     g = _load(golden_dir, "composite.npz")
     n_rays = int(g["n_rays"])
