@@ -17,9 +17,7 @@ import argparse
 import gc
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -130,10 +128,10 @@ def run_reference(args, w, rank, world):
     see DESIGN.md) on the host cores, bounded sample per step."""
     if rank != 0:
         return
-    n_cpu = 1024 if args.workload != "tiny" else 256
+    n_cpu = 8192 if args.workload != "tiny" else 256                  # ~1.5 s of CPU work per step on 16 cores
     for _ in range(min(args.warmup, 1)):
         cpu_oracle_step_time(w, n_cpu, 1)
-    t, n_pre, n_kept = cpu_oracle_step_time(w, n_cpu, max(1, min(args.steps, 3)))
+    t, n_pre, n_kept = cpu_oracle_step_time(w, n_cpu, max(1, min(args.steps, 8)))
     val = n_cpu / t
     line = {"impl": "reference", "metric": "train_rays_per_s", "value": val, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -317,10 +315,12 @@ def main():
                     pass
         cpu = None
         if not args.no_cpu_baseline:
-            n_cpu = 1024 if args.workload != "tiny" else 256
-            t_cpu, cp, ck = cpu_oracle_step_time(w, n_cpu, 1)
+            n_cpu, n_cpu_steps = (8192, 6) if args.workload != "tiny" else (256, 2)   # ~10 s of CPU work on the box's host cores
+            cpu_oracle_step_time(w, n_cpu, 1)                                          # untimed warm-up (thread pools, allocator)
+            t_cpu, cp, ck = cpu_oracle_step_time(w, n_cpu, n_cpu_steps)
             cpu = {"value": n_cpu / t_cpu, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"one {n_cpu}-ray training step of the oracle port ({cp} marched / {ck} kept samples, {t_cpu:.1f} s)"}
+                   "sample": f"{n_cpu_steps} training steps of {n_cpu} rays of the oracle port ({cp} marched / {ck} kept samples per step, "
+                             f"{t_cpu:.2f} s per step)"}
         rays = R * world * args.steps
         line = {"metric": "train_rays_per_s", "value": rays / (ms * 1e-3), "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
