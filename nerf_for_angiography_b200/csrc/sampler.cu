@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) sample_candidates_kernel(const float* __r
 }
 
 // ---- pass 2: exact selection + shuffle over the m ~ n + 8 sqrt(n) candidates (L2 resident)
-//   select_kernel   (1 CTA)    radix select of the n-th smallest key -> ctl[1] = its bit pattern, ctl[2] = ties to take
+//   radix_hist_kernel x3 + select_finish_kernel: radix select of the n-th smallest key -> ctl[1] = its bit pattern, ctl[2] = ties to take
 //   mark_kernel     (many CTAs) flag the sample (the flag is the ray's shuffle hash, it replaces the key) + bucket histogram
 //   scatter_kernel  (many CTAs) every CTA scans the <= 4096 bucket counts itself, then scatters (hash, id) into its bucket
 //   bucket_sort_kernel (warp per bucket) orders each ~32-ray bucket by (hash, id) and writes the final ids
@@ -71,63 +71,99 @@ __device__ __forceinline__ uint32_t shuffle_hash(int64_t id, uint64_t seed) {
 }
 
 // ctl: [0] candidate counter, [1] threshold key bits, [2] ties to take, [3] ties taken
-__global__ void __launch_bounds__(kSelThreads, 1) select_kernel(const float* __restrict__ cand_keys, int32_t* __restrict__ ctl, int32_t capacity,
-                                                                int32_t n, int32_t* __restrict__ status) {
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_prefix, s_need;
+// Exact radix select of the n-th smallest key (keys are positive floats: their bit patterns order like the values), most
+// significant bits first in three passes of 12 + 12 + 8 bits.  Each pass is a multi-CTA histogram into a global table; a CTA of
+// the next pass first locates the bin that holds the wanted rank in the previous tables (<= 4096 bins: one block scan), so no
+// pass needs a separate "find" launch.  (The single-CTA version of this took 79 us; the winning keys share their leading bits,
+// hence the warp-aggregated shared-memory histogram.)
+__host__ __device__ constexpr int hist_bits(int pass) { return pass == 2 ? 8 : 12; }
+__host__ __device__ constexpr int hist_shift(int pass) { return pass == 0 ? 20 : (pass == 1 ? 8 : 0); }
+__host__ __device__ constexpr int hist_off(int pass) { return pass == 0 ? 0 : (pass == 1 ? 4096 : 8192); }
+constexpr int kHistWords = 4096 + 4096 + 256;
+
+// all kSelThreads threads: bin and remaining rank such that cum(bin - 1) < need <= cum(bin); nbins <= 4096
+__device__ __forceinline__ void find_bin(const uint32_t* __restrict__ hist, int nbins, uint32_t need, uint32_t* s_scan, uint32_t* s_out) {
   const int tid = threadIdx.x;
+  uint32_t v[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { const int bin = tid * 4 + k; v[k] = (bin < nbins) ? hist[bin] : 0u; sum += v[k]; }
+  uint32_t inc = sum;
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += t; }
+  if ((tid & 31) == 31) s_scan[tid / 32] = inc;
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t w = s_scan[tid], winc = w;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o); if (tid >= o) winc += t; }
+    s_scan[tid] = winc - w;
+  }
+  __syncthreads();
+  uint32_t cum = s_scan[tid / 32] + inc - sum;           // keys in the bins before this thread's four
+  if (cum < need && need <= cum + sum) {
+    int k = 0;
+    for (; k < 4; ++k) { if (cum + v[k] >= need) break; cum += v[k]; }
+    s_out[0] = (uint32_t)(tid * 4 + k);
+    s_out[1] = need - cum;
+  }
+  __syncthreads();
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kSelThreads) radix_hist_kernel(const float* __restrict__ cand_keys, const int32_t* __restrict__ ctl,
+                                                                int32_t capacity, int32_t n, uint32_t* __restrict__ hists) {
+  __shared__ uint32_t s_hist[4096];
+  __shared__ uint32_t s_scan[32];
+  __shared__ uint32_t s_out[2];
+  const int tid = threadIdx.x;
+  const int m = min(ctl[0], capacity);
+  if (m < n) return;
+  uint32_t prefix = 0;                                    // bits already fixed by the earlier passes (right-aligned)
+  if (PASS >= 1) {
+    find_bin(hists + hist_off(0), 1 << hist_bits(0), (uint32_t)n, s_scan, s_out);
+    prefix = s_out[0];
+    if (PASS >= 2) {
+      const uint32_t need1 = s_out[1];
+      __syncthreads();
+      find_bin(hists + hist_off(1), 1 << hist_bits(1), need1, s_scan, s_out);
+      prefix = (prefix << hist_bits(1)) | s_out[0];
+    }
+  }
+  constexpr int nb = 1 << hist_bits(PASS);
+  for (int b = tid; b < nb; b += kSelThreads) s_hist[b] = 0;
+  __syncthreads();
+  const uint32_t* kb = reinterpret_cast<const uint32_t*>(cand_keys);
+  for (int i0 = blockIdx.x * kSelThreads; i0 < m; i0 += gridDim.x * kSelThreads) {
+    const int i = i0 + tid;
+    const uint32_t b = (i < m) ? kb[i] : 0u;
+    const bool hit = (i < m) && (PASS == 0 || (b >> (hist_shift(PASS) + hist_bits(PASS))) == prefix);
+    const uint32_t digit = hit ? (b >> hist_shift(PASS)) & (uint32_t)(nb - 1) : 0xFFFFFFFFu;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    if (hit && (tid & 31) == __ffs(peers) - 1) atomicAdd(&s_hist[digit], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  for (int b = tid; b < nb; b += kSelThreads)
+    if (s_hist[b]) atomicAdd(&hists[hist_off(PASS) + b], s_hist[b]);
+}
+
+// one CTA: the three bins -> threshold bit pattern + ties to take; also the status words of the call
+__global__ void __launch_bounds__(kSelThreads) select_finish_kernel(int32_t* __restrict__ ctl, int32_t capacity, int32_t n,
+                                                                   const uint32_t* __restrict__ hists, int32_t* __restrict__ status) {
+  __shared__ uint32_t s_scan[32];
+  __shared__ uint32_t s_out[2];
   const int count = ctl[0];
   const int m = min(count, capacity);
-  const uint32_t* kb = reinterpret_cast<const uint32_t*>(cand_keys);   // keys are positive floats: their bit patterns order like the values
-  if (tid == 0) {
-    s_prefix = 0; s_need = (uint32_t)n;
+  if (threadIdx.x == 0) {
     status[0] = count;
     status[1] = (count > capacity || m < n) ? 1 : 0;        // overflow / too few candidates: the caller re-draws with a larger tau
   }
-  __syncthreads();
   if (m < n) return;
-  uint32_t mask = 0;
-  for (int pass = 0; pass < 4; ++pass) {                     // MSB first, 8 bits per pass
-    const int shift = 24 - 8 * pass;
-    if (tid < 256) hist[tid] = 0;
-    __syncthreads();
-    const uint32_t prefix = s_prefix;
-    for (int i0 = 0; i0 < m; i0 += 4 * kSelThreads) {
-      uint32_t b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {                     // four independent loads in flight per thread
-        const int i = i0 + u * kSelThreads + tid;
-        b[u] = (i < m) ? kb[i] : 0xFFFFFFFFu;           // keys are finite positive floats: never all ones
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool hit = (b[u] != 0xFFFFFFFFu) && ((b[u] & mask) == prefix);
-        // warp-aggregated histogram: the winning keys share their leading bits, so a plain atomicAdd serialises on one bin
-        const uint32_t digit = hit ? (b[u] >> shift) & 255u : 256u;
-        const unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (hit && (tid & 31) == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
-      }
-    }
-    __syncthreads();
-    if (tid < 32) {                                          // warp 0 finds the digit that holds the s_need-th key
-      const uint32_t need = s_need;
-      uint32_t loc[8], sum = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { loc[k] = hist[tid * 8 + k]; sum += loc[k]; }
-      uint32_t inc = sum;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
-      uint32_t cum = inc - sum;                              // keys in the digits before this lane's 8
-      if (cum < need && need <= inc) {
-        int d = 0;
-        for (; d < 8; ++d) { if (cum + loc[d] >= need) break; cum += loc[d]; }
-        s_need = need - cum;
-        s_prefix = prefix | ((uint32_t)(tid * 8 + d) << shift);
-      }
-    }
-    mask |= 255u << shift;
+  uint32_t prefix = 0, need = (uint32_t)n;
+  for (int pass = 0; pass < 3; ++pass) {
+    find_bin(hists + hist_off(pass), 1 << hist_bits(pass), need, s_scan, s_out);
+    prefix = (prefix << hist_bits(pass)) | s_out[0];
+    need = s_out[1];
     __syncthreads();
   }
-  if (tid == 0) { ctl[1] = (int32_t)s_prefix; ctl[2] = (int32_t)s_need; ctl[3] = 0; }
+  if (threadIdx.x == 0) { ctl[1] = (int32_t)prefix; ctl[2] = (int32_t)need; ctl[3] = 0; }
 }
 
 __device__ __forceinline__ uint32_t bucket_of(uint32_t flag, int log2_buckets) { return log2_buckets ? flag >> (32 - log2_buckets) : 0u; }
@@ -283,7 +319,7 @@ extern "C" int angio_sample_candidates(const float* weights, int64_t n_pool, uin
 extern "C" int64_t angio_sample_rays_workspace_bytes(int32_t capacity, int64_t n) {
   if (capacity <= 0 || n < 0) return ANGIO_ERR_INVALID_ARG;
   // control words + bucket counters | candidate keys | candidate ids | bucketed hashes | bucketed ids
-  return align256(16 + (3 * kMaxBuckets + 1) * 4) + align256((int64_t)capacity * 4) + align256((int64_t)capacity * 8) + align256(n * 4) +
+  return align256(16 + (3 * kMaxBuckets + 1 + kHistWords) * 4) + align256((int64_t)capacity * 4) + align256((int64_t)capacity * 8) + align256(n * 4) +
          align256(n * 8);
 }
 
@@ -298,23 +334,27 @@ extern "C" int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n
   }
   cudaStream_t st = angio::as_stream(stream);
   char* wb = reinterpret_cast<char*>(workspace);
-  const int64_t head = align256(16 + (3 * kMaxBuckets + 1) * 4);
+  const int64_t head = align256(16 + (3 * kMaxBuckets + 1 + kHistWords) * 4);
   int32_t* ctl = reinterpret_cast<int32_t*>(wb);
   uint32_t* bcount = reinterpret_cast<uint32_t*>(wb + 16);
   uint32_t* bfill = bcount + kMaxBuckets;
-  uint32_t* bstart = bfill + kMaxBuckets;
+  uint32_t* hists = bfill + kMaxBuckets;                               // zeroed together with the counters
+  uint32_t* bstart = hists + kHistWords;
   wb += head;
   float* keys = reinterpret_cast<float*>(wb); wb += align256((int64_t)capacity * 4);
   int64_t* ids = reinterpret_cast<int64_t*>(wb); wb += align256((int64_t)capacity * 8);
   uint32_t* tmp_hash = reinterpret_cast<uint32_t*>(wb); wb += align256(n * 4);
   int64_t* tmp_ids = reinterpret_cast<int64_t*>(wb);
-  ANGIO_CUDA(cudaMemsetAsync(ctl, 0, 16 + 2 * kMaxBuckets * 4, st));   // counters, bucket counts and fills
+  ANGIO_CUDA(cudaMemsetAsync(ctl, 0, 16 + (2 * kMaxBuckets + kHistWords) * 4, st));   // counters, bucket counts / fills, radix histograms
   if (int rc = angio_sample_candidates(weights, n_pool, seed, tau, capacity, keys, ids, ctl, stream)) return rc;
   int n_buckets = 1, log2b = 0;                                        // ~32 rays per shuffle bucket
   while (n_buckets < kMaxBuckets && (int64_t)n_buckets * 32 < n) { n_buckets <<= 1; ++log2b; }
   int sweep_blocks = angio::blocks_for(capacity, 1024);
   if (sweep_blocks > angio::sm_count()) sweep_blocks = angio::sm_count();
-  angio::note_launch(); select_kernel<<<1, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, status);
+  angio::note_launch(); radix_hist_kernel<0><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
+  angio::note_launch(); radix_hist_kernel<1><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
+  angio::note_launch(); radix_hist_kernel<2><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
+  angio::note_launch(); select_finish_kernel<<<1, kSelThreads, 0, st>>>(ctl, capacity, (int32_t)n, hists, status);
   angio::note_launch(); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, seed, log2b, bcount);
   angio::note_launch(); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, n_buckets, log2b, bcount, bfill,
                                                                           bstart, tmp_hash, tmp_ids);
