@@ -240,47 +240,47 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
   }
 }
 
-// Single-block exclusive scan of per-ray counts (n = rays per batch: 64 K .. 1 M), 32 K elements per round.
-// Global loads and stores are lane-contiguous 16-byte accesses; the round is staged in shared memory with a stride-33 padding
-// so that each thread can then walk ITS 32 consecutive elements conflict-free (thread-contiguous global accesses -- 32 lines
-// per warp instruction -- made the single SM's L1 the bottleneck: 9 us per round).  One shuffle scan over the 1024 thread
-// totals per round.
-constexpr int kScanPerThread = 32;
-constexpr int kScanRound = 1024 * kScanPerThread;
-constexpr int kScanSmemBytes = (kScanRound + kScanRound / 32) * 4;
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ counts, int64_t n,
-                                                              int32_t* __restrict__ offsets, int32_t* __restrict__ total_out) {
-  extern __shared__ int32_t s_buf[];            // element e of the round lives at s_buf[e + e / 32]
+// Exclusive scan of per-ray counts (n = rays per batch: 64 K .. 1 M) by ONE thread-block cluster of 8 CTAs (portable cluster
+// size): a round covers 8 x 1024 x 8 = 64 K elements -- a whole config-3 batch -- with lane-contiguous 32-byte loads / stores,
+// the CTA totals are exchanged through distributed shared memory (every CTA writes its total into all eight CTAs' shared
+// memory), one cluster barrier, no global scratch and no second launch.  (A single CTA needed two 9 us rounds for 64 K counts.)
+constexpr int kScanCtas = 8;
+constexpr int kScanPerThread = 8;
+constexpr int kScanRound = kScanCtas * 1024 * kScanPerThread;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_cluster(uint32_t local_smem_addr, uint32_t cta, int32_t v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta));
+  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(kScanCtas, 1, 1) __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __restrict__ counts, int64_t n,
+                                                                                                 int32_t* __restrict__ offsets,
+                                                                                                 int32_t* __restrict__ total_out) {
   __shared__ int32_t s_warp[32];
-  __shared__ int32_t s_carry;
+  __shared__ int32_t s_cta_tot[2][kScanCtas];     // [round parity][cta]: written by every CTA of the cluster (DSMEM)
   const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
-  if (tid == 0) s_carry = 0;
-  __syncthreads();
+  const uint32_t cta = cluster_ctarank();
   const bool vec_ok = (reinterpret_cast<uintptr_t>(counts) % 16 == 0) && (reinterpret_cast<uintptr_t>(offsets) % 16 == 0);
-  for (int64_t base = 0; base < n; base += kScanRound) {
-    // ---- coalesced load of the round into shared memory
-#pragma unroll
-    for (int k = 0; k < kScanPerThread / 4; ++k) {
-      const int e = (k * 1024 + tid) * 4;
-      int4 q = make_int4(0, 0, 0, 0);
-      if (vec_ok && base + e + 4 <= n) {
-        q = *reinterpret_cast<const int4*>(counts + base + e);
-      } else {
-        if (base + e < n) q.x = counts[base + e];
-        if (base + e + 1 < n) q.y = counts[base + e + 1];
-        if (base + e + 2 < n) q.z = counts[base + e + 2];
-        if (base + e + 3 < n) q.w = counts[base + e + 3];
-      }
-      int32_t* d = s_buf + e + e / 32;          // four consecutive elements never straddle a padding slot
-      d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
-    }
-    __syncthreads();
-    // ---- each thread scans its 32 consecutive elements (row `tid` of the padded buffer)
-    int32_t* row = s_buf + tid * 33;
+  int32_t carry = 0;                               // sum of all earlier rounds (every thread of every CTA tracks it)
+  int round = 0;
+  for (int64_t base = 0; base < n; base += kScanRound, ++round) {
+    const int64_t i0 = base + ((int64_t)cta * 1024 + tid) * kScanPerThread;
     int32_t v[kScanPerThread];
+    if (vec_ok && i0 + kScanPerThread <= n) {
+      const int4 q0 = *reinterpret_cast<const int4*>(counts + i0), q1 = *reinterpret_cast<const int4*>(counts + i0 + 4);
+      v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < kScanPerThread; ++k) v[k] = (i0 + k < n) ? counts[i0 + k] : 0;
+    }
     int32_t local = 0;
 #pragma unroll
-    for (int k = 0; k < kScanPerThread; ++k) { v[k] = local; local += row[k]; }
+    for (int k = 0; k < kScanPerThread; ++k) { const int32_t t = v[k]; v[k] = local; local += t; }   // exclusive within the thread
     int32_t incl = local;
 #pragma unroll
     for (int s = 1; s < 32; s <<= 1) {
@@ -297,31 +297,36 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(const int32_t* __r
         const int32_t t = __shfl_up_sync(0xffffffffu, wi, s);
         if (lane >= s) wi += t;
       }
-      s_warp[lane] = wi - w;  // exclusive prefix of warp sums
-    }
-    __syncthreads();
-    const int32_t pre = s_carry + s_warp[warp] + incl - local;
-#pragma unroll
-    for (int k = 0; k < kScanPerThread; ++k) row[k] = pre + v[k];
-    __syncthreads();
-    if (tid == 1023) s_carry = pre + local;
-    // ---- coalesced store
-#pragma unroll
-    for (int k = 0; k < kScanPerThread / 4; ++k) {
-      const int e = (k * 1024 + tid) * 4;
-      const int32_t* d = s_buf + e + e / 32;
-      if (vec_ok && base + e + 4 <= n) {
-        *reinterpret_cast<int4*>(offsets + base + e) = make_int4(d[0], d[1], d[2], d[3]);
-      } else {
-        for (int u = 0; u < 4; ++u)
-          if (base + e + u < n) offsets[base + e + u] = d[u];
+      s_warp[lane] = wi - w;                       // exclusive prefix of warp sums
+      if (lane == 31) {                            // wi = this CTA's total: publish it to every CTA of the cluster
+        const uint32_t slot = (uint32_t)__cvta_generic_to_shared(&s_cta_tot[round & 1][cta]);
+        for (uint32_t c = 0; c < kScanCtas; ++c) st_shared_cluster(slot, c, wi);
       }
     }
-    __syncthreads();
+    cluster_sync_all();                            // all eight totals are in everybody's shared memory (also a CTA barrier)
+    int32_t before = 0, all = 0;
+#pragma unroll
+    for (int c = 0; c < kScanCtas; ++c) {
+      const int32_t t = s_cta_tot[round & 1][c];
+      if (c < (int)cta) before += t;
+      all += t;
+    }
+    const int32_t pre = carry + before + s_warp[warp] + incl - local;
+    if (vec_ok && i0 + kScanPerThread <= n) {
+      *reinterpret_cast<int4*>(offsets + i0) = make_int4(pre + v[0], pre + v[1], pre + v[2], pre + v[3]);
+      *reinterpret_cast<int4*>(offsets + i0 + 4) = make_int4(pre + v[4], pre + v[5], pre + v[6], pre + v[7]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < kScanPerThread; ++k)
+        if (i0 + k < n) offsets[i0 + k] = pre + v[k];
+    }
+    carry += all;
+    __syncthreads();                               // s_warp is rewritten next round (s_cta_tot alternates by parity)
   }
-  if (tid == 0) {
-    offsets[n] = s_carry;
-    if (total_out) *total_out = s_carry;
+  cluster_sync_all();                              // no CTA exits while a peer may still write into its shared memory
+  if (cta == 0 && tid == 0) {
+    offsets[n] = carry;
+    if (total_out) *total_out = carry;
   }
 }
 
@@ -369,12 +374,7 @@ extern "C" int64_t angio_march_runs_bytes(int64_t n_rays) { return n_rays < 0 ? 
 
 extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out, void* stream) {
   ANGIO_REQUIRE(offsets && (counts || n == 0) && n >= 0, "angio_exclusive_scan_i32: bad arguments");
-  static bool configured = false;
-  if (!configured) {
-    ANGIO_CUDA(cudaFuncSetAttribute(exclusive_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanSmemBytes));
-    configured = true;
-  }
-  angio::note_launch(); exclusive_scan_kernel<<<1, 1024, kScanSmemBytes, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
+  angio::note_launch(); exclusive_scan_kernel<<<kScanCtas, 1024, 0, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
   return angio::finish_launch("angio_exclusive_scan_i32");
 }
 
