@@ -282,19 +282,6 @@ __device__ __forceinline__ void load_weight_image(uint8_t* smem, const uint8_t* 
 
 // Epilogue body of one layer for one warp: 64 accumulator columns of this thread's row -> + bias -> ReLU -> bf16x2 words
 // (PACK) and, for the last hidden layer (LAST), this half's share of the output dot product  w_out . relu(z)  in fp32.
-// 32 accumulator columns -> + bias -> ReLU -> 16 bf16x2 words
-template <class Out>
-__device__ __forceinline__ void bias_relu_chunk(const uint32_t (&r)[32], const float* __restrict__ bias, Out& pk) {
-#pragma unroll
-  for (int jj = 0; jj < 8; ++jj) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * jj);
-    const float2 u0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1])), make_float2(b.x, b.y));
-    const float2 u1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3])), make_float2(b.z, b.w));
-    pk[2 * jj] = pack_bf16x2_relu(u0.x, u0.y);
-    pk[2 * jj + 1] = pack_bf16x2_relu(u1.x, u1.y);
-  }
-}
-
 template <bool LAST, bool PACK>
 __device__ __forceinline__ float bias_relu_math(const uint32_t (&r0)[32], const uint32_t (&r1)[32], const float* __restrict__ bias,
                                                 const float* __restrict__ w_out, uint32_t (&pk)[32]) {
@@ -470,19 +457,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
         fence_after_sync();
         if (lane == 0 && (warp - 2) % 8 == 0) trace_event(2, g, l, (int)(j / 2));
         uint32_t pk[32];
-        {
-          // two 32-column chunks: the second TMEM load is in flight while the first chunk is biased, packed and stored
-          const float* bias = consts + l * 128 + h * 64;
-          uint32_t r0[32], r1[32];
-          tmem_ld32(acc_tmem, r0);
-          wait_ld();
-          tmem_ld32(acc_tmem + 32, r1);
-          bias_relu_chunk(r0, bias, pk);
-          tmem_st16(a_tmem + h * 32, *reinterpret_cast<const uint32_t(*)[16]>(&pk[0]));
-          wait_ld();
-          bias_relu_chunk(r1, bias + 32, *reinterpret_cast<uint32_t(*)[16]>(&pk[16]));
-          tmem_st16(a_tmem + h * 32 + 16, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16]));
-        }
+        bias_relu_pack<false, true>(acc_tmem, consts + l * 128 + h * 64, nullptr, pk);
+        tmem_st32(a_tmem + h * 32, pk);
         signal_a_ready(&bars.a_ready[g], lane);
         if (TRAIN) {   // after the hand-off: the tile-image / mask stores drain while the tensor core runs the next layer
           store_rows_staged(stage, saved + lay_tiles * kA0Bytes + ((int64_t)l * lay_tiles + tile) * kActBytes + h * 16384, q, row, lane, pk);
