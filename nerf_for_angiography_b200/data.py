@@ -124,10 +124,10 @@ class RayPool:
         N, dev = self.n_rays, self.device
         if n > N:
             raise ValueError("cannot sample more rays than the pool holds without replacement")
-        w = self.weights if weights is None else weights
+        w = self.weights if weights is None else (None if isinstance(weights, str) and weights == "uniform" else weights)
         if w is not None:
             wf = w.reshape(-1).contiguous().float()
-            if weights is not None:
+            if weights is not None and not isinstance(weights, str):
                 wsum, wsum2 = float(wf.sum().item()), float((wf.double() ** 2).sum().item())
             else:
                 if self._wsum is None:
@@ -152,6 +152,57 @@ class RayPool:
     def sample(self, n, weights=None, generator=None, status=None):
         """status: optional int32[2] device tensor receiving [candidates, overflow flag] (see ops.sample_without_replacement)."""
         return self.gather(self.sample_ids(n, weights=weights, generator=generator, status=status))
+
+
+class ExplicitRayPool:
+    """Device-resident copy of a reference ray DataFrame (one row per ray with precomputed origins / directions, the layout
+    `run_nerf_acc.py:113-117` samples from): o[N,3], d[N,3], pixel_value[N] and any number of named weight columns.  Lets
+    `sample_pixel_rays(train_ray_df, ...)` keep the reference's DataFrame signature while the draw itself runs in the sampler
+    kernels; prefer `RayPool` (rays regenerated from (view, x, y)) when the projection matrices are known."""
+
+    def __init__(self, rays_o, rays_d, pixel_values, weights=None):
+        self.o = rays_o.contiguous().float()
+        self.d = rays_d.contiguous().float()
+        self.pix = pixel_values.contiguous().float()
+        self.weight_columns = {k: v.contiguous().float() for k, v in (weights or {}).items()}
+        self.n_rays = self.o.shape[0]
+        self._wsum, self._seed_streams, self._bufs, self.last_status = {}, {}, ops.BufferPool(), None
+
+    @classmethod
+    def from_dataframe(cls, ray_df, device="cuda", weight_columns=("distance_pixel_value",)):
+        def col3(prefix):
+            if f"{prefix}_x" in ray_df.columns:
+                a = np.stack([ray_df[f"{prefix}_{c}"].to_numpy(dtype=np.float64) for c in "xyz"], axis=1)
+            else:
+                a = np.asarray(ray_df[prefix].tolist(), dtype=np.float64)
+            return torch.from_numpy(a.astype(np.float32)).to(device)      # the reference casts with .float() / torch.Tensor(...)
+        w = {c: torch.from_numpy(ray_df[c].to_numpy(dtype=np.float64).astype(np.float32)).to(device) for c in weight_columns if c in ray_df.columns}
+        pix = torch.from_numpy(ray_df["pixel_value"].to_numpy(dtype=np.float64).astype(np.float32)).to(device)
+        return cls(col3("ray_origins"), col3("ray_directions"), pix, w)
+
+    @property
+    def device(self):
+        return self.o.device
+
+    @torch.no_grad()
+    def sample(self, n, weights=None, generator=None, status=None):
+        """weights: None (uniform) or the name of a weight column, like DataFrame.sample(n, weights=<column>)."""
+        if n > self.n_rays:
+            raise ValueError("cannot sample more rays than the pool holds without replacement")
+        wf, wsum, wsum2 = None, float(self.n_rays), float(self.n_rays)
+        if weights is not None:
+            wf = self.weight_columns[weights]
+            if weights not in self._wsum:
+                self._wsum[weights] = (float(wf.sum().item()), float((wf.double() ** 2).sum().item()))
+            wsum, wsum2 = self._wsum[weights]
+        key = id(generator) if generator is not None else None
+        rng = self._seed_streams.get(key)
+        if rng is None:
+            rng = np.random.default_rng(generator.initial_seed() if generator is not None else None)
+            self._seed_streams[key] = rng
+        ids, self.last_status = ops.sample_without_replacement(n, self.n_rays, wf, wsum, wsum2, int(rng.integers(0, 2 ** 62)), self.device,
+                                                               pool=self._bufs, status=status)
+        return self.o[ids], self.d[ids], self.pix[ids]
 
 
 def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0, 135.0), kind="ct", volume_res=128,

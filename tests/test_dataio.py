@@ -65,3 +65,23 @@ def test_pool_from_reference_dataframes(tmp_path):
     bad["tform_cam2world"] = [np.eye(4).tolist()] * 3
     with pytest.raises(ValueError):
         dataio.pool_from_dataframes(bad, ray_df, device="cuda")
+
+
+@pytest.mark.gpu
+def test_sample_pixel_rays_accepts_the_reference_dataframe(tmp_path):
+    """run_nerf_acc.py:277 calls sample_pixel_rays(train_ray_df, n, device, weights=<column name>): same call, DataFrame in,
+    device tensors out, rows drawn without replacement and consistent with the frame."""
+    import nerf_for_angiography_b200 as A
+    dataio, views, mats, images, dist, o, d, paths, W, H, focal = _tiny_dataset(str(tmp_path))
+    proj_df, ray_df = dataio.read_reference_csvs(*paths)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    bo, bd, bp = A.sample_pixel_rays(ray_df, 40, "cuda", weights="distance_pixel_value", generator=g)
+    assert bo.shape == (40, 3) and bd.shape == (40, 3) and bp.shape == (40,) and bo.is_cuda
+    rows = ray_df[["ray_directions_x", "ray_directions_y", "ray_directions_z"]].to_numpy().astype(np.float32)
+    pix = ray_df["pixel_value"].to_numpy().astype(np.float32)
+    hit = [int(np.flatnonzero((rows == r).all(1) & (pix == p))[0]) for r, p in zip(bd.cpu().numpy(), bp.cpu().numpy())]
+    assert len(set(hit)) == 40                                                                # 40 distinct rows of the frame
+    assert "_angio_pool" in ray_df.attrs                                                      # copied to the device once
+    bo2, bd2, bp2 = A.sample_pixel_rays(ray_df, 90, "cuda", weights=None, unseen=True, generator=g)
+    assert bp2 is None and bo2.shape == (90, 3)                                               # all 90 rays: a permutation
+    assert np.array_equal(np.sort(bd2.cpu().numpy(), axis=0), np.sort(rows, axis=0))
