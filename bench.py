@@ -327,10 +327,14 @@ def main():
                 "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "detector": f"{w['img']}x{w['img']}", "views": len(w["thetas"]) + 1,
                            "mlp": f"{w['L']}x{w['H']} {w['enc']}", "rays_per_gpu_per_step": R, "march_steps": 300, "grid": "128^3",
-                           "l2": "no flush: every step draws fresh rays and streams ~15 M marched samples (>= 250 MB of sample "
-                                 "arrays), larger than the 126 MB L2",
+                           "iterations": [args.warmup, args.warmup + args.steps],
+                           "l2": "no flush: every step draws fresh rays and streams the saved bf16 tile images of its kept samples "
+                                 f"(~1 KB/sample x {n_kept_total / max(args.steps, 1) / 1e6:.1f} M samples/step here) plus the sample arrays "
+                                 "through HBM, far more than the 126 MB L2",
                            "visibility_pass": "every marched sample (reference order)" if args.full_visibility else
-                                              "two-phase with early ray termination (kept samples bit-identical to evaluating every sample)"},
+                                              "early ray termination: first 32 samples of every ray, then only the rays still transparent "
+                                              + ("(marched lazily as well) " if tr.lazy_march else "") +
+                                              "-- kept samples bit-identical to evaluating every sample"},
                 "mlp_evals_visibility_per_step": float(sum(kernel_n)) / max(args.steps, 1),
                 "samples_per_s_marched": float(cnt[0]) / (ms * 1e-3), "samples_per_s_kept": float(cnt[1]) / (ms * 1e-3),
                 "clocks": clk, "gpu_launches": launches,

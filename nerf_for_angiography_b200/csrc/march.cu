@@ -122,17 +122,26 @@ __global__ void __launch_bounds__(128) march_count_kernel(const float* __restric
                                                           float far_plane, float* __restrict__ t_min,
                                                           float* __restrict__ t_max, int32_t* __restrict__ counts,
                                                           float* __restrict__ run_t0, float* __restrict__ run_t1,
-                                                          int32_t* __restrict__ run_n, int32_t* __restrict__ n_runs) {
+                                                          int32_t* __restrict__ run_n, int32_t* __restrict__ n_runs,
+                                                          const uint8_t* __restrict__ resume_alive) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rays) return;
   float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
   float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
   float a, b;
-  ray_aabb(o, d, aabb.v, a, b);
-  a = a < near_plane ? near_plane : a;  // torch.clamp(t_min, min=near_plane)
-  b = b > far_plane ? far_plane : b;    // torch.clamp(t_max, max=far_plane)
-  t_min[i] = a;
-  t_max[i] = b;
+  if (resume_alive) {
+    // continuation of a head march (march_head_kernel): t_min / t_max are INPUTS -- the head stopped right after emitting a
+    // sample, where the marcher's state (t0, t0 + dt, their midpoint) is exactly what init() builds from t_min = that t0
+    if (!resume_alive[i]) { counts[i] = 0; if (n_runs) n_runs[i] = 0; return; }
+    a = t_min[i];
+    b = t_max[i];
+  } else {
+    ray_aabb(o, d, aabb.v, a, b);
+    a = a < near_plane ? near_plane : a;  // torch.clamp(t_min, min=near_plane)
+    b = b > far_plane ? far_plane : b;    // torch.clamp(t_max, max=far_plane)
+    t_min[i] = a;
+    t_max[i] = b;
+  }
   Marcher m;
   m.init(o, d, a, b, p.dt);
   // Runs: maximal stretches of consecutive samples (t0 of a sample = t1 of the one before).  The first kMaxRuns of a ray are
@@ -237,6 +246,51 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
     }
     written += cnt;
     __syncwarp();
+  }
+}
+
+// Lazy marching, head pass: the first k0 (<= 32) samples of every ray in a ray-strided layout (sample j of ray r at r * k0 + j),
+// one pass, no count / scan: with early ray termination most rays never need more (a dense field is opaque after a few
+// samples, a pruned grid leaves few samples per ray), and the rays that do continue from t_resume with the ordinary
+// count -> scan -> write passes (angio_march_count with resume_alive).  Same Marcher, so head + tail are the samples of the full
+// march, bit for bit.  The warp stages its 32 rays' samples in shared memory and flushes one 128-byte row per ray.
+__global__ void __launch_bounds__(32 * kWarpsPerBlock) march_head_kernel(
+    const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays, Aabb6 aabb, MarchParams p,
+    const uint8_t* __restrict__ binary, float near_plane, float far_plane, int k0, float* __restrict__ head_t0, float* __restrict__ head_t1,
+    int32_t* __restrict__ head_cnt, float* __restrict__ t_resume, float* __restrict__ t_max) {
+  __shared__ float s_t0[kWarpsPerBlock][32][kStagePad];
+  __shared__ float s_t1[kWarpsPerBlock][32][kStagePad];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t ray0 = (blockIdx.x * (int64_t)kWarpsPerBlock + warp) * 32;
+  if (ray0 >= n_rays) return;
+  const int64_t i = ray0 + lane;
+  float(*st0)[kStagePad] = s_t0[warp];
+  float(*st1)[kStagePad] = s_t1[warp];
+  int cnt = 0;
+  if (i < n_rays) {
+    float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
+    float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
+    float a, b;
+    ray_aabb(o, d, aabb.v, a, b);
+    a = a < near_plane ? near_plane : a;
+    b = b > far_plane ? far_plane : b;
+    Marcher m;
+    m.init(o, d, a, b, p.dt);
+    cnt = m.advance(p, binary, k0, [&](int j, float t0, float t1) { st0[lane][j] = t0; st1[lane][j] = t1; }, []() {});
+    head_cnt[i] = cnt;
+    // budget reached: the last action was an emit, the state is init(t0); otherwise the ray is finished
+    t_resume[i] = (cnt == k0) ? m.t0 : b;
+    t_max[i] = b;
+  }
+  __syncwarp();
+#pragma unroll 1
+  for (int r = 0; r < 32; ++r) {
+    const int c = __shfl_sync(0xffffffffu, cnt, r);
+    if (lane < c) {
+      const int64_t dst = (ray0 + r) * k0 + lane;
+      head_t0[dst] = st0[r][lane];
+      head_t1[dst] = st1[r][lane];
+    }
   }
 }
 
@@ -358,7 +412,7 @@ MarchParams make_params(const float* roi_host, int res, float dt) {
 extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host,
                                  const float* roi_host, int32_t res, const uint8_t* binary, float near_plane,
                                  float far_plane, float step_size, float* t_min, float* t_max, int32_t* counts,
-                                 void* runs, void* stream) {
+                                 void* runs, const uint8_t* resume_alive, void* stream) {
   ANGIO_REQUIRE(rays_o && rays_d && aabb_host && roi_host && binary && t_min && t_max && counts, "angio_march_count: null pointer");
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_count: bad sizes (step_size must be > 0)");
   if (n_rays == 0) return 0;
@@ -366,8 +420,24 @@ extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
   angio::note_launch(); march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts,
-      run_table_t0(runs, n_rays), run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays));
+      run_table_t0(runs, n_rays), run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays), resume_alive);
   return angio::finish_launch("angio_march_count");
+}
+
+extern "C" int angio_march_head(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host, const float* roi_host,
+                                int32_t res, const uint8_t* binary, float near_plane, float far_plane, float step_size, int32_t k0,
+                                float* head_t0, float* head_t1, int32_t* head_cnt, float* t_resume, float* t_max, void* stream) {
+  ANGIO_REQUIRE(rays_o && rays_d && aabb_host && roi_host && binary && head_t0 && head_t1 && head_cnt && t_resume && t_max,
+                "angio_march_head: null pointer");
+  ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f && k0 >= 1 && k0 <= kStage, "angio_march_head: bad sizes (1 <= k0 <= 32)");
+  if (n_rays == 0) return 0;
+  Aabb6 aabb;
+  for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
+  const int rays_per_block = 32 * kWarpsPerBlock;
+  angio::note_launch(); march_head_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
+      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, k0, head_t0, head_t1, head_cnt, t_resume,
+      t_max);
+  return angio::finish_launch("angio_march_head");
 }
 
 extern "C" int64_t angio_march_runs_bytes(int64_t n_rays) { return n_rays < 0 ? ANGIO_ERR_INVALID_ARG : (3 * (int64_t)kMaxRuns + 1) * n_rays * 4; }

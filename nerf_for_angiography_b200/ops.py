@@ -161,7 +161,7 @@ def march(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, 
     runs = _alloc(pool, tag + "_runs", int(lib.angio_march_runs_bytes(R)), torch.uint8, dev) if use_runs else None
     _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
                                      float(near_plane), float(far_plane), float(step_size), _p(t_min), _p(t_max), _p(counts),
-                                     _p(runs), _stream()), "angio_march_count")
+                                     _p(runs), None, _stream()), "angio_march_count")
     offsets = exclusive_scan(counts, total_out)
     n = int(offsets[-1].item()) if capacity is None else int(capacity)
     ray_idx = _alloc(pool, tag + "_idx", n, torch.int32, dev)
@@ -221,7 +221,7 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     keep = _alloc(pool, "vis_keep", n, torch.uint8, dev)
     kept = torch.empty((R,), dtype=torch.int32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(alphas), _p(offsets), R, float(early_stop_eps), float(alpha_thre), _p(keep), _p(kept),
-                                         _stream()), "angio_visibility_mask")
+                                         None, None, _stream()), "angio_visibility_mask")
     host_totals = None
     if capacity is not None:
         new_offsets = exclusive_scan(kept, totals[1:2] if totals is not None else None)
@@ -285,6 +285,118 @@ def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t
             _lib.check(lib.angio_visibility_head(_p(alphas), _p(offsets), R, int(k0), float(early_stop_eps), _p(alive), _stream()),
                        "angio_visibility_head")
     return alphas, evaluated
+
+
+def march_head(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size, k0=32, pool=None):
+    """First k0 (<= 32) samples of every ray in ONE marching pass, ray-strided (sample j of ray r at r * k0 + j): returns
+    (head_t0, head_t1, head_cnt, t_resume, t_max).  Depends on the occupancy grid only, not on the model."""
+    lib = _lib.load()
+    if not 1 <= k0 <= 32:
+        raise ValueError("k0 must be in 1..32")
+    rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
+    rays_d = _chk(rays_d, torch.float32, "ray_directions", 2)
+    binary = _bin_u8(binary, resolution)
+    aabb = _host6(scene_aabb, "scene_aabb")
+    roi = _host6(roi_aabb, "roi_aabb")
+    R, dev = rays_o.shape[0], rays_o.device
+    h_t0 = _alloc(pool, "lz_h_t0", R * k0, torch.float32, dev)
+    h_t1 = _alloc(pool, "lz_h_t1", R * k0, torch.float32, dev)
+    h_cnt = torch.empty((R,), dtype=torch.int32, device=dev)
+    t_res = torch.empty((R,), dtype=torch.float32, device=dev)
+    t_max = torch.empty((R,), dtype=torch.float32, device=dev)
+    _lib.check(lib.angio_march_head(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
+                                    float(near_plane), float(far_plane), float(step_size), int(k0), _p(h_t0), _p(h_t1), _p(h_cnt), _p(t_res),
+                                    _p(t_max), _stream()), "angio_march_head")
+    return h_t0, h_t1, h_cnt, t_res, t_max
+
+
+def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane,
+                      step_size, early_stop_eps, alpha_thre, k0=32, totals=None, pool=None, timing=None, head=None):
+    """acc_ray_marching (march -> alpha_fn -> visibility filter -> compaction) with LAZY marching and no host sync:
+
+      head   the first k0 samples of every ray, one marching pass into a ray-strided layout (no count / scan), alpha by the MLP
+             straight from that layout, visibility of the head, and which rays are still alive behind it;
+      tail   only for those rays: count -> scan -> write from where the head stopped, alpha, visibility continuing the head's
+             transmittance;
+      then   one scan of the kept counts and one compaction of head + tail into the packed layout.
+
+    The kept samples are bit-identical to marching every ray to the end and filtering afterwards (the reference's order); rays
+    that are opaque after k0 samples -- or simply have no more -- never pay for the rest.  Returns (ray_idx, t_starts, t_ends,
+    offsets) with capacity-sized arrays, the kept count in offsets[R]; totals (int32[>=2] device tensor) receives
+    [samples marched (head + tail), samples kept].  `head` = the result of march_head for the same rays / grid / k0 when it was
+    computed ahead of time (it does not depend on the model)."""
+    lib = _lib.load()
+    if precision != PREC_BF16:
+        raise ValueError("march_filter_lazy: bf16 path only")
+    if not 1 <= k0 <= 32:
+        raise ValueError("k0 must be in 1..32")
+    rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
+    rays_d = _chk(rays_d, torch.float32, "ray_directions", 2)
+    binary = _bin_u8(binary, resolution)
+    aabb = _host6(scene_aabb, "scene_aabb")
+    roi = _host6(roi_aabb, "roi_aabb")
+    R, dev = rays_o.shape[0], rays_o.device
+    cap = march_capacity(R, near_plane, far_plane, step_size)
+    i32, f32, u8 = torch.int32, torch.float32, torch.uint8
+    # ---- head
+    if head is None:
+        head = march_head(rays_o, rays_d, aabb, roi, resolution, binary, near_plane, far_plane, step_size, k0=k0, pool=pool)
+    h_t0, h_t1, h_cnt, t_res, t_max = head
+    if h_t0.numel() < R * k0 or h_cnt.numel() != R:
+        raise ValueError("march_filter_lazy: `head` does not belong to these rays / this k0")
+    h_alpha = _alloc(pool, "lz_h_alpha", R * k0, f32, dev)
+    h_keep = _alloc(pool, "lz_h_keep", R * k0, u8, dev)
+    h_kept = torch.empty((R,), dtype=i32, device=dev)
+    t_end = torch.empty((R,), dtype=f32, device=dev)
+    alive = torch.empty((R,), dtype=u8, device=dev)
+    marched = torch.zeros((2,), dtype=i32, device=dev)                       # [head samples, tail samples]
+    if timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    s = Samples(R * k0, None, _p(rays_o), _p(rays_d), None, _p(h_t0), _p(h_t1), None, _p(h_cnt), int(k0), None)
+    _lib.check(lib.angio_mlp_forward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), OUT_ALPHA, PREC_BF16, _p(h_alpha), None,
+                                     None, 0, _stream()), "angio_mlp_forward")
+    if timing is not None:
+        ev1.record()
+        timing.append((ev0, ev1, marched[0:1]))
+    _lib.check(lib.angio_visibility_head_mask(_p(h_alpha), _p(h_cnt), R, int(k0), float(early_stop_eps), float(alpha_thre), _p(h_keep),
+                                              _p(h_kept), _p(t_end), _p(alive), _p(marched), _stream()), "angio_visibility_head_mask")
+    # ---- tail of the rays that are still alive (usually few; the kernels do nothing for the others)
+    counts = torch.empty((R,), dtype=i32, device=dev)
+    runs = _alloc(pool, "lz_runs", int(lib.angio_march_runs_bytes(R)), u8, dev)
+    _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
+                                     float(near_plane), float(far_plane), float(step_size), _p(t_res), _p(t_max), _p(counts), _p(runs),
+                                     _p(alive), _stream()), "angio_march_count")
+    t_off = exclusive_scan(counts, marched[1:2])
+    t_idx = _alloc(pool, "lz_t_idx", cap, i32, dev)
+    t_t0 = _alloc(pool, "lz_t_t0", cap, f32, dev)
+    t_t1 = _alloc(pool, "lz_t_t1", cap, f32, dev)
+    t_alpha = _alloc(pool, "lz_t_alpha", cap, f32, dev)
+    t_keep = _alloc(pool, "lz_t_keep", cap, u8, dev)
+    _lib.check(lib.angio_march_write(_p(rays_o), _p(rays_d), R, roi.ctypes.data, int(resolution), _p(binary), float(step_size), _p(t_res),
+                                     _p(t_max), _p(t_off), _p(runs), cap, _p(t_idx), _p(t_t0), _p(t_t1), _stream()), "angio_march_write")
+    if timing is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    s = Samples(cap, None, _p(rays_o), _p(rays_d), _p(t_idx), _p(t_t0), _p(t_t1), None, None, 0, _p(t_off[R:R + 1]))
+    _lib.check(lib.angio_mlp_forward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), OUT_ALPHA, PREC_BF16, _p(t_alpha), None,
+                                     None, 0, _stream()), "angio_mlp_forward")
+    if timing is not None:
+        ev1.record()
+        timing.append((ev0, ev1, marched[1:2]))
+    kept = torch.empty((R,), dtype=i32, device=dev)
+    _lib.check(lib.angio_visibility_mask(_p(t_alpha), _p(t_off), R, float(early_stop_eps), float(alpha_thre), _p(t_keep), _p(kept), _p(t_end),
+                                         _p(h_kept), _stream()), "angio_visibility_mask")
+    # ---- packed result
+    new_off = exclusive_scan(kept, totals[1:2] if totals is not None else None)
+    ray_idx = _alloc(pool, "kept_idx", cap, i32, dev)
+    t0 = _alloc(pool, "kept_t0", cap, f32, dev)
+    t1 = _alloc(pool, "kept_t1", cap, f32, dev)
+    _lib.check(lib.angio_compact_head_tail(_p(h_keep), _p(h_cnt), _p(h_t0), _p(h_t1), int(k0), _p(t_keep), _p(t_off), _p(t_t0), _p(t_t1),
+                                           _p(new_off), R, cap, _p(ray_idx), _p(t0), _p(t1), _stream()), "angio_compact_head_tail")
+    if totals is not None:
+        torch.add(marched[0:1], marched[1:2], out=totals[0:1])
+    return ray_idx, t0, t1, new_off
 
 
 # ------------------------------------------------------------------------------------------------ composite
@@ -371,7 +483,7 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
     sample_idx = _chk(sample_idx, torch.int32, "sample_idx", 1, allow_none=True)
     if sample_idx is not None:
         n = sample_idx.numel()
-    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(sample_idx), _p(n_dev))
+    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(sample_idx), None, 0, _p(n_dev))
     return s, n
 
 

@@ -101,6 +101,9 @@ class Trainer:
         # visibility pass with early ray termination (bf16 path): number of leading samples per ray evaluated before the rays
         # that are already opaque are dropped (multiple of 32); 0 / None = evaluate every marched sample like the reference
         self.early_termination = int(early_termination) if early_termination else 0
+        # lazy marching (sync-free loop with early termination): march only the first samples of every ray before the
+        # visibility pass and the rest only for rays that are still transparent behind them.  ANGIO_LAZY_MARCH=0: full march.
+        self.lazy_march = bool(self.sync_free and self.early_termination and os.environ.get("ANGIO_LAZY_MARCH", "1") != "0")
 
     # ------------------------------------------------------------------ memory plan
     def _plan_memory(self, mode, fraction):
@@ -141,6 +144,10 @@ class Trainer:
         """Marcher only (bf16 path: capacity-sized arrays, count left on the device in offsets[R] and totals[0])."""
         g = self.acc_grid
         bf16 = self.model._precision_id == ops.PREC_BF16
+        if pooled and self.lazy_march and o.shape[0] <= self.n_rays:
+            # lazy marching: only the head of every ray is independent of the model (the tail follows the visibility of the head)
+            return ops.march_head(o, d, self._aabb_host, g._roi_host, g._resolution, g._binary_u8(), self.near, self.far, self.step_size,
+                                  k0=min(32, self.early_termination), pool=self.pool_bufs)
         cap = ops.march_capacity(o.shape[0], self.near, self.far, self.step_size) if bf16 else None
         # sync-free mode: pooled arrays, two alternating sets because a prefetched batch is alive next to the current one
         pool, tag = None, "march"
@@ -174,6 +181,12 @@ class Trainer:
         cap = ops.march_capacity(R, self.near, self.far, self.step_size) if bf16 else None
         if bf16 and totals is None:
             totals = torch.zeros((4,), dtype=torch.int32, device=o.device)
+        if sync_free and self.lazy_march:                # `marched`, if given, is the head march of these rays (see _march)
+            ray_idx, t0, t1, offsets = ops.march_filter_lazy(
+                self.model._desc, self.kflat, self.packed, self.model._precision_id, o, d, self._aabb_host, g._roi_host, g._resolution,
+                g._binary_u8(), self.near, self.far, self.step_size, self.early_stop_eps, min(self.alpha_thre, g.occs_mean_host),
+                k0=min(32, self.early_termination), totals=totals, pool=self.pool_bufs, timing=self.kernel_events, head=marched)
+            return ray_idx, t0, t1, offsets, None
         ray_idx, t0, t1, offsets = marched if marched is not None else self._march(o, d, totals, pooled=sync_free)
         n_pre = ray_idx.numel()
         if n_pre > 0:
@@ -302,7 +315,9 @@ class Trainer:
         for g, (occs, binary, mean) in zip(grids, snap["grids"]):
             g.occs.copy_(occs); g._binary.copy_(binary); g.occs_mean_host = mean
         self.ray_gen.set_state(snap["gens"][0]); self.grid_gen.set_state(snap["gens"][1])
-        self._prefetched = snap.get("prefetched")
+        # the pending batch keeps its rays (own tensors); its march lived in pooled arrays that later steps have reused -> redo it
+        pre = snap.get("prefetched")
+        self._prefetched = dict(pre, marched=None) if pre is not None else None
         if snap.get("seed_stream") is not None:
             rng = np.random.default_rng(0)
             rng.bit_generator.state = snap["seed_stream"]

@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--start-iter", type=int, default=257)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--train-steps", type=int, default=4, help="training steps before the captured ones (the field thins out as it trains)")
+    ap.add_argument("--merge", action="store_true", help="print per-kernel totals instead of every launch")
     args = ap.parse_args()
     w = bench.WORKLOADS[args.workload]
     rank, local, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -34,9 +36,10 @@ def main():
     pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], kind="ct", volume_res=w["vol"], device=dev)
     model = A.CPPN(bench.model_def(w, dev, args.precision)).to(dev)
     tr = Trainer(model, pool, info["near"], info["far"], n_rays=w["rays"])
-    for _ in range(4):
+    for _ in range(args.train_steps):
         tr.step()
-    tr.n_iter = args.start_iter
+    if args.start_iter >= 0:
+        tr.n_iter = args.start_iter
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(args.steps):
@@ -56,12 +59,19 @@ def main():
     end_prev = t0
     busy = 0.0
     print(f"{'start_us':>10} {'dur_us':>9} {'gap_us':>8}  kernel")
+    merged = {}
     for e in evs:
         s, d = e.time_range.start - t0, e.time_range.end - e.time_range.start
         gap = e.time_range.start - end_prev
         busy += d
         end_prev = max(end_prev, e.time_range.end)
-        print(f"{s:10.1f} {d:9.1f} {gap:8.1f}  {e.name[:90]}")
+        if args.merge:
+            m = merged.setdefault(e.name[:90], [0, 0.0])
+            m[0] += 1; m[1] += d
+        else:
+            print(f"{s:10.1f} {d:9.1f} {gap:8.1f}  {e.name[:90]}")
+    for name, (n, d) in sorted(merged.items(), key=lambda kv: -kv[1][1]):
+        print(f"{d / args.steps:10.1f} us/step {n / args.steps:6.1f} launches/step  {name}")
     total = end_prev - t0
     print(f"steps={args.steps} span={total / 1e3:.3f} ms busy={busy / 1e3:.3f} ms ({100 * busy / total:.1f}%) per-step span={total / 1e3 / args.steps:.3f} ms")
 
