@@ -94,14 +94,18 @@ ANGIO_API int angio_march_count(const float* rays_o, const float* rays_d, int64_
                       const float* roi_host, int32_t res, const uint8_t* binary, float near_plane,
                       float far_plane, float step_size, float* t_min, float* t_max, int32_t* counts,
                       void* runs, const uint8_t* resume_alive, void* stream);
-/* Lazy marching.  angio_march_head marches only the first k0 (<= 32) samples of every ray, in ONE pass and into a ray-strided
- * layout (sample j of ray r at r * k0 + j, head_cnt[r] of them), and leaves t_resume / t_max per ray.  With early ray
- * termination most rays need nothing more; the others are continued with angio_march_count(resume_alive = their flags,
- * t_min = t_resume and t_max as INPUTS) -> scan -> angio_march_write: head + tail are exactly the samples of the full march. */
+/* Lazy marching.  angio_march_head marches only the first k0 (<= 32) samples of every ray, in ONE pass: ray r gets head_cnt[r]
+ * samples in slots head_base[r] ... of head_idx / head_t0 / head_t1 (capacity n_rays * k0).  The samples are packed without a
+ * scan -- every warp reserves the slots of its 32 rays with one atomic add on *head_total, which must be 0 on entry and holds
+ * the number of head samples afterwards -- so the ORDER of the rays in memory is unspecified; everything downstream goes
+ * through head_base.  t_resume / t_max per ray: with early ray termination most rays need nothing more; the others are
+ * continued with angio_march_count(resume_alive = their flags, t_min = t_resume and t_max as INPUTS) -> scan ->
+ * angio_march_write: head + tail are exactly the samples of the full march. */
 ANGIO_API int angio_march_head(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host,
                      const float* roi_host, int32_t res, const uint8_t* binary, float near_plane, float far_plane,
-                     float step_size, int32_t k0, float* head_t0, float* head_t1, int32_t* head_cnt,
-                     float* t_resume, float* t_max, void* stream);
+                     float step_size, int32_t k0, int32_t* head_idx, float* head_t0, float* head_t1,
+                     int32_t* head_cnt, int32_t* head_base, int32_t* head_total, float* t_resume, float* t_max,
+                     void* stream);
 /* exclusive scan: offsets[n+1] int32 (offsets[n] = total); also copies the total to *total_out if not NULL */
 ANGIO_API int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out,
                              void* stream);
@@ -127,18 +131,18 @@ ANGIO_API int angio_grid_query(const float* points, int64_t n, const float* roi_
 ANGIO_API int angio_visibility_mask(const float* alphas, const int32_t* offsets, int64_t n_rays,
                           float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts,
                           const float* t_init, const int32_t* base_counts, void* stream);
-/* Visibility of ray-strided head samples (angio_march_head layout): keep flags, kept count, transmittance behind the head
- * (t_end) and alive[r] = the head used its whole budget and t_end >= early_stop_eps (the ray must be continued);
- * head_total (optional, device int) accumulates sum(head_cnt). */
-ANGIO_API int angio_visibility_head_mask(const float* alphas, const int32_t* head_cnt, int64_t n_rays, int32_t k0,
-                               float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts,
-                               float* t_end, uint8_t* alive, int32_t* head_total, void* stream);
+/* Visibility of the head samples of angio_march_head: keep flags (indexed like the head arrays), kept count, transmittance
+ * behind the head (t_end) and alive[r] = the head used its whole budget and t_end >= early_stop_eps (the ray must be
+ * continued). */
+ANGIO_API int angio_visibility_head_mask(const float* alphas, const int32_t* head_cnt, const int32_t* head_base,
+                               int64_t n_rays, int32_t k0, float early_stop_eps, float alpha_thre, uint8_t* keep,
+                               int32_t* kept_counts, float* t_end, uint8_t* alive, void* stream);
 /* Compaction of a lazily marched batch into the packed layout: per ray the kept head samples, then the kept tail samples. */
-ANGIO_API int angio_compact_head_tail(const uint8_t* keep_head, const int32_t* head_cnt, const float* head_t0,
-                            const float* head_t1, int32_t k0, const uint8_t* keep_tail, const int32_t* tail_offsets,
-                            const float* tail_t0, const float* tail_t1, const int32_t* new_offsets, int64_t n_rays,
-                            int64_t capacity, int32_t* ray_idx_out, float* t_starts_out, float* t_ends_out,
-                            void* stream);
+ANGIO_API int angio_compact_head_tail(const uint8_t* keep_head, const int32_t* head_cnt, const int32_t* head_base,
+                            const float* head_t0, const float* head_t1, const uint8_t* keep_tail,
+                            const int32_t* tail_offsets, const float* tail_t0, const float* tail_t1,
+                            const int32_t* new_offsets, int64_t n_rays, int64_t capacity, int32_t* ray_idx_out,
+                            float* t_starts_out, float* t_ends_out, void* stream);
 /* Two-phase visibility pass (early ray termination; the kept set is bit-identical to evaluating every sample): phase A
  * evaluates the first k0 samples of every ray, angio_visibility_head marks the rays whose transmittance after them is still
  * >= early_stop_eps, phase B evaluates the remaining samples of those rays only.  The sample subsets are handed to
@@ -187,10 +191,6 @@ typedef struct angio_samples {
   const int32_t* sample_idx; /* optional [n] index list: sample k of this call is element sample_idx[k] of ray_idx /
                                 t_starts / t_ends, and its output goes to out[sample_idx[k]] (inference forward of the
                                 bf16 path only; NULL = identity) */
-  const int32_t* head_cnt;   /* optional "ray-strided head" layout (angio_march_head): sample k of this call belongs to ray
-                                k / head_k, is its (k % head_k)-th sample and exists iff that is < head_cnt[ray]; t_starts /
-                                t_ends are indexed by k, ray_idx is not read.  n = n_rays * head_k.  bf16 inference forward. */
-  int32_t head_k;
   const int32_t* n_dev;   /* optional DEVICE-resident sample count: kernels process min(*n_dev, n) samples, so a marcher
                              that leaves its total on the device can feed the MLP without a host sync (n = capacity of
                              the arrays; tile-image layouts of the saved activations are strided by that capacity).

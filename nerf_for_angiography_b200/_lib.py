@@ -19,7 +19,7 @@ class MlpDesc(ctypes.Structure):
 class Samples(ctypes.Structure):
     """angio_samples"""
     _fields_ = [("n", c_i64), ("points", c_ptr), ("rays_o", c_ptr), ("rays_d", c_ptr), ("ray_idx", c_ptr),
-                ("t_starts", c_ptr), ("t_ends", c_ptr), ("sample_idx", c_ptr), ("head_cnt", c_ptr), ("head_k", c_i32), ("n_dev", c_ptr)]
+                ("t_starts", c_ptr), ("t_ends", c_ptr), ("sample_idx", c_ptr), ("n_dev", c_ptr)]
 
 
 _P_DESC = ctypes.POINTER(MlpDesc)
@@ -38,13 +38,14 @@ PROTOTYPES = {
     "angio_raygen": (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_march_runs_bytes": (c_i64, [c_i64]),
     "angio_march_count": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "angio_march_head": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_march_head": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_ptr, c_f32, c_f32, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                  c_ptr]),
     "angio_exclusive_scan_i32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "angio_march_write": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_grid_query": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
     "angio_visibility_mask": (c_i32, [c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "angio_visibility_head_mask": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "angio_compact_head_tail": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_visibility_head_mask": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_compact_head_tail": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_counts": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_ids": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
     "angio_visibility_head": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_f32, c_ptr, c_ptr]),

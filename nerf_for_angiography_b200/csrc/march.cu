@@ -249,15 +249,18 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
   }
 }
 
-// Lazy marching, head pass: the first k0 (<= 32) samples of every ray in a ray-strided layout (sample j of ray r at r * k0 + j),
-// one pass, no count / scan: with early ray termination most rays never need more (a dense field is opaque after a few
-// samples, a pruned grid leaves few samples per ray), and the rays that do continue from t_resume with the ordinary
-// count -> scan -> write passes (angio_march_count with resume_alive).  Same Marcher, so head + tail are the samples of the full
-// march, bit for bit.  The warp stages its 32 rays' samples in shared memory and flushes one 128-byte row per ray.
+// Lazy marching, head pass: the first k0 (<= 32) samples of every ray, one pass, no count / scan: with early ray termination
+// most rays never need more (a dense field is opaque after a few samples, a pruned grid leaves few samples per ray), and the
+// rays that do continue from t_resume with the ordinary count -> scan -> write passes (angio_march_count with resume_alive).
+// Same Marcher, so head + tail are the samples of the full march, bit for bit.  The samples are PACKED without a scan: a warp
+// sums its 32 rays' counts, reserves that many slots with one atomicAdd on the running total and records each ray's first
+// slot in head_base -- the order of the rays in memory depends on the order the warps arrive, every consumer goes through
+// head_base, so results do not.  The warp stages its rays' samples in shared memory and flushes one ray segment per round.
 __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_head_kernel(
     const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays, Aabb6 aabb, MarchParams p,
-    const uint8_t* __restrict__ binary, float near_plane, float far_plane, int k0, float* __restrict__ head_t0, float* __restrict__ head_t1,
-    int32_t* __restrict__ head_cnt, float* __restrict__ t_resume, float* __restrict__ t_max) {
+    const uint8_t* __restrict__ binary, float near_plane, float far_plane, int k0, int32_t* __restrict__ head_idx,
+    float* __restrict__ head_t0, float* __restrict__ head_t1, int32_t* __restrict__ head_cnt, int32_t* __restrict__ head_base,
+    int32_t* __restrict__ head_total, float* __restrict__ t_resume, float* __restrict__ t_max) {
   __shared__ float s_t0[kWarpsPerBlock][32][kStagePad];
   __shared__ float s_t1[kWarpsPerBlock][32][kStagePad];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -282,12 +285,27 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_head_kernel(
     t_resume[i] = (cnt == k0) ? m.t0 : b;
     t_max[i] = b;
   }
+  // slots of this warp's rays: inclusive warp scan of the counts, one atomic reservation per warp
+  int incl = cnt;
+#pragma unroll
+  for (int s = 1; s < 32; s <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, s);
+    if (lane >= s) incl += v;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  int warp_base = 0;
+  if (lane == 0 && warp_total > 0) warp_base = atomicAdd(head_total, warp_total);
+  warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+  const int my_base = warp_base + incl - cnt;
+  if (i < n_rays) head_base[i] = my_base;
   __syncwarp();
 #pragma unroll 1
   for (int r = 0; r < 32; ++r) {
     const int c = __shfl_sync(0xffffffffu, cnt, r);
+    if (c == 0) continue;
+    const int dst = __shfl_sync(0xffffffffu, my_base, r) + lane;
     if (lane < c) {
-      const int64_t dst = (ray0 + r) * k0 + lane;
+      head_idx[dst] = (int32_t)(ray0 + r);
       head_t0[dst] = st0[r][lane];
       head_t1[dst] = st1[r][lane];
     }
@@ -426,8 +444,10 @@ extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64
 
 extern "C" int angio_march_head(const float* rays_o, const float* rays_d, int64_t n_rays, const float* aabb_host, const float* roi_host,
                                 int32_t res, const uint8_t* binary, float near_plane, float far_plane, float step_size, int32_t k0,
-                                float* head_t0, float* head_t1, int32_t* head_cnt, float* t_resume, float* t_max, void* stream) {
-  ANGIO_REQUIRE(rays_o && rays_d && aabb_host && roi_host && binary && head_t0 && head_t1 && head_cnt && t_resume && t_max,
+                                int32_t* head_idx, float* head_t0, float* head_t1, int32_t* head_cnt, int32_t* head_base, int32_t* head_total,
+                                float* t_resume, float* t_max, void* stream) {
+  ANGIO_REQUIRE(rays_o && rays_d && aabb_host && roi_host && binary && head_idx && head_t0 && head_t1 && head_cnt && head_base &&
+                    head_total && t_resume && t_max,
                 "angio_march_head: null pointer");
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f && k0 >= 1 && k0 <= kStage, "angio_march_head: bad sizes (1 <= k0 <= 32)");
   if (n_rays == 0) return 0;
@@ -435,8 +455,8 @@ extern "C" int angio_march_head(const float* rays_o, const float* rays_d, int64_
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
   const int rays_per_block = 32 * kWarpsPerBlock;
   angio::note_launch(); march_head_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
-      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, k0, head_t0, head_t1, head_cnt, t_resume,
-      t_max);
+      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, k0, head_idx, head_t0, head_t1,
+      head_cnt, head_base, head_total, t_resume, t_max);
   return angio::finish_launch("angio_march_head");
 }
 

@@ -25,7 +25,7 @@ using angio::MlpLayout;
 
 static int check_samples(const angio_samples* in, const char* who) {
   if (!in || in->n < 0) { angio::set_error("%s: bad sample descriptor", who); return ANGIO_ERR_INVALID_ARG; }
-  if (in->n > 0 && !in->points && !(in->rays_o && in->rays_d && (in->ray_idx || in->head_cnt) && in->t_starts && in->t_ends)) {
+  if (in->n > 0 && !in->points && !(in->rays_o && in->rays_d && in->ray_idx && in->t_starts && in->t_ends)) {
     angio::set_error("%s: need either points or (rays_o, rays_d, ray_idx, t_starts, t_ends)", who);
     return ANGIO_ERR_INVALID_ARG;
   }
@@ -84,10 +84,6 @@ extern "C" int angio_mlp_forward(const angio_mlp_desc* desc, const float* params
     angio::set_error("angio_mlp_forward: a device-resident sample count (n_dev) is only supported by the bf16 path");
     return ANGIO_ERR_UNSUPPORTED;
   }
-  if (in->head_cnt && (precision != ANGIO_PREC_BF16 || saved || in->points || in->sample_idx || in->head_k < 1)) {
-    angio::set_error("angio_mlp_forward: the ray-strided head layout is only supported by the bf16 inference forward on ray samples");
-    return ANGIO_ERR_UNSUPPORTED;
-  }
   if (in->sample_idx && (precision != ANGIO_PREC_BF16 || saved || in->points)) {
     angio::set_error("angio_mlp_forward: sample_idx is only supported by the bf16 inference forward on ray samples");
     return ANGIO_ERR_UNSUPPORTED;
@@ -112,7 +108,7 @@ extern "C" int angio_mlp_backward(const angio_mlp_desc* desc, const float* param
   if (int rc = check_samples(in, "angio_mlp_backward")) return rc;
   ANGIO_REQUIRE(in->n == 0 || (saved && grad_out), "angio_mlp_backward: needs saved activations and grad_out");
   ANGIO_REQUIRE(!in->n_dev || precision == ANGIO_PREC_BF16, "angio_mlp_backward: n_dev is only supported by the bf16 path");
-  ANGIO_REQUIRE(!in->sample_idx && !in->head_cnt, "angio_mlp_backward: sample_idx / head layout are not supported");
+  ANGIO_REQUIRE(!in->sample_idx, "angio_mlp_backward: sample_idx is not supported");
   if (precision == ANGIO_PREC_FP32)
     return angio::simt_backward(L, params, *in, saved, grad_out, grad_params, workspace, workspace_bytes, angio::as_stream(stream));
   if (precision == ANGIO_PREC_BF16) {

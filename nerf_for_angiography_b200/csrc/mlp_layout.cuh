@@ -44,7 +44,7 @@ __device__ __forceinline__ void sample_position(const angio_samples& in, int64_t
   if (in.points) {
     x[0] = in.points[i * 3]; x[1] = in.points[i * 3 + 1]; x[2] = in.points[i * 3 + 2];
   } else {
-    const int r = in.head_cnt ? (int)(i / in.head_k) : in.ray_idx[i];   // ray-strided head layout: the ray is implied by the slot
+    const int r = in.ray_idx[i];
     const float ts = __fadd_rn(in.t_starts[i], in.t_ends[i]);
 #pragma unroll
     for (int k = 0; k < 3; ++k)

@@ -410,7 +410,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
       vv = (jt < my_tiles) && (ii < n);
       xx[0] = xx[1] = xx[2] = 0.f;
       dtt = 0.f;
-      if (vv && in.head_cnt) vv = (int)(ii % in.head_k) < in.head_cnt[ii / in.head_k];   // ray-strided head layout: unused slots
       if (vv) {
         if (in.sample_idx) ii = in.sample_idx[ii];      // index list: a subset of the sample arrays (two-phase visibility pass)
         angio::sample_position(in, ii, xx);

@@ -82,21 +82,21 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict_
   }
 }
 
-// ---- lazily marched rays (march_head_kernel): visibility of the ray-strided head samples.  One warp per ray, k0 <= 32 samples =
-// one chunk of the chain above.  Besides the keep flags and the kept count it leaves the transmittance behind the head and
-// whether the ray has to be continued: only if its head used the whole budget (more samples may follow) and it is not opaque yet.
+// ---- lazily marched rays (march_head_kernel): visibility of the head samples (ray r: head_cnt[r] <= k0 <= 32 samples from slot
+// head_base[r]).  One warp per ray, one chunk of the chain above.  Besides the keep flags and the kept count it leaves the
+// transmittance behind the head and whether the ray has to be continued: only if its head used the whole budget (more samples
+// may follow) and it is not opaque yet.
 __global__ void __launch_bounds__(256) visibility_head_mask_kernel(const float* __restrict__ alphas, const int32_t* __restrict__ head_cnt,
-                                                                   int64_t n_rays, int k0, float eps, float thre, uint8_t* __restrict__ keep,
-                                                                   int32_t* __restrict__ kept_counts, float* __restrict__ t_end,
-                                                                   uint8_t* __restrict__ alive, int32_t* __restrict__ head_total) {
+                                                                   const int32_t* __restrict__ head_base, int64_t n_rays, int k0, float eps,
+                                                                   float thre, uint8_t* __restrict__ keep, int32_t* __restrict__ kept_counts,
+                                                                   float* __restrict__ t_end, uint8_t* __restrict__ alive) {
   const int lane = threadIdx.x % 32;
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
-  int local_total = 0;
   for (int64_t r = warp_global; r < n_rays; r += n_warps) {
-    const int cnt = head_cnt[r];
+    const int cnt = head_cnt[r], base = head_base[r];
     const bool valid = lane < cnt;
-    const float a = valid ? alphas[r * k0 + lane] : 0.0f;
+    const float a = valid ? alphas[base + lane] : 0.0f;
     float T = 1.0f, myT = 1.0f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -106,21 +106,20 @@ __global__ void __launch_bounds__(256) visibility_head_mask_kernel(const float* 
     }
     bool vis = valid && (myT >= eps);
     if (thre > 0.0f) vis = vis && (a >= thre);
-    if (lane < k0) keep[r * k0 + lane] = vis ? 1 : 0;
+    if (valid) keep[base + lane] = vis ? 1 : 0;
     const int kept = __popc(__ballot_sync(0xffffffffu, vis));
     if (lane == 0) {
       kept_counts[r] = kept;
       t_end[r] = T;
       alive[r] = (cnt == k0 && T >= eps) ? 1 : 0;
-      local_total += cnt;
     }
   }
-  if (head_total && lane == 0 && local_total) atomicAdd(head_total, local_total);
 }
 
-// compaction of a lazily marched batch: kept head samples (ray-strided) first, then the kept tail samples (packed), per ray
+// compaction of a lazily marched batch: kept head samples first, then the kept tail samples (packed by tail_offsets), per ray
 __global__ void __launch_bounds__(256) compact_head_tail_kernel(const uint8_t* __restrict__ keep_head, const int32_t* __restrict__ head_cnt,
-                                                                const float* __restrict__ head_t0, const float* __restrict__ head_t1, int k0,
+                                                                const int32_t* __restrict__ head_base, const float* __restrict__ head_t0,
+                                                                const float* __restrict__ head_t1,
                                                                 const uint8_t* __restrict__ keep_tail, const int32_t* __restrict__ tail_offsets,
                                                                 const float* __restrict__ tail_t0, const float* __restrict__ tail_t1,
                                                                 const int32_t* __restrict__ new_offsets, int64_t n_rays, int64_t capacity,
@@ -134,13 +133,14 @@ __global__ void __launch_bounds__(256) compact_head_tail_kernel(const uint8_t* _
     const int dst_end = new_offsets[r + 1];
     if (dst == dst_end) continue;
     {
-      const bool k = lane < head_cnt[r] && keep_head[r * k0 + lane];
+      const int hb = head_base[r];
+      const bool k = lane < head_cnt[r] && keep_head[hb + lane];
       const unsigned m = __ballot_sync(0xffffffffu, k);
       const int pos = dst + __popc(m & ((1u << lane) - 1u));
       if (k && pos < capacity) {
         ray_idx_out[pos] = (int32_t)r;
-        t0_out[pos] = head_t0[r * k0 + lane];
-        t1_out[pos] = head_t1[r * k0 + lane];
+        t0_out[pos] = head_t0[hb + lane];
+        t1_out[pos] = head_t1[hb + lane];
       }
       dst += __popc(m);
     }
@@ -246,28 +246,28 @@ extern "C" int angio_visibility_head(const float* alphas, const int32_t* offsets
   return angio::finish_launch("angio_visibility_head");
 }
 
-extern "C" int angio_visibility_head_mask(const float* alphas, const int32_t* head_cnt, int64_t n_rays, int32_t k0, float early_stop_eps,
-                                          float alpha_thre, uint8_t* keep, int32_t* kept_counts, float* t_end, uint8_t* alive,
-                                          int32_t* head_total, void* stream) {
-  ANGIO_REQUIRE(alphas && head_cnt && keep && kept_counts && t_end && alive && n_rays >= 0 && k0 >= 1 && k0 <= 32,
+extern "C" int angio_visibility_head_mask(const float* alphas, const int32_t* head_cnt, const int32_t* head_base, int64_t n_rays, int32_t k0,
+                                          float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts, float* t_end,
+                                          uint8_t* alive, void* stream) {
+  ANGIO_REQUIRE(alphas && head_cnt && head_base && keep && kept_counts && t_end && alive && n_rays >= 0 && k0 >= 1 && k0 <= 32,
                 "angio_visibility_head_mask: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); visibility_head_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, head_cnt, n_rays, k0, early_stop_eps,
-                                                                                                    alpha_thre, keep, kept_counts, t_end, alive, head_total);
+  angio::note_launch(); visibility_head_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
+      alphas, head_cnt, head_base, n_rays, k0, early_stop_eps, alpha_thre, keep, kept_counts, t_end, alive);
   return angio::finish_launch("angio_visibility_head_mask");
 }
 
-extern "C" int angio_compact_head_tail(const uint8_t* keep_head, const int32_t* head_cnt, const float* head_t0, const float* head_t1, int32_t k0,
-                                       const uint8_t* keep_tail, const int32_t* tail_offsets, const float* tail_t0, const float* tail_t1,
-                                       const int32_t* new_offsets, int64_t n_rays, int64_t capacity, int32_t* ray_idx_out, float* t_starts_out,
-                                       float* t_ends_out, void* stream) {
-  ANGIO_REQUIRE(keep_head && head_cnt && head_t0 && head_t1 && tail_offsets && new_offsets && ray_idx_out && t_starts_out && t_ends_out &&
-                    n_rays >= 0 && k0 >= 1 && k0 <= 32,
+extern "C" int angio_compact_head_tail(const uint8_t* keep_head, const int32_t* head_cnt, const int32_t* head_base, const float* head_t0,
+                                       const float* head_t1, const uint8_t* keep_tail, const int32_t* tail_offsets, const float* tail_t0,
+                                       const float* tail_t1, const int32_t* new_offsets, int64_t n_rays, int64_t capacity,
+                                       int32_t* ray_idx_out, float* t_starts_out, float* t_ends_out, void* stream) {
+  ANGIO_REQUIRE(keep_head && head_cnt && head_base && head_t0 && head_t1 && tail_offsets && new_offsets && ray_idx_out && t_starts_out &&
+                    t_ends_out && n_rays >= 0,
                 "angio_compact_head_tail: bad arguments");
   if (n_rays == 0) return 0;
   angio::note_launch(); compact_head_tail_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
-      keep_head, head_cnt, head_t0, head_t1, k0, keep_tail, tail_offsets, tail_t0, tail_t1, new_offsets, n_rays, capacity > 0 ? capacity : INT64_MAX,
-      ray_idx_out, t_starts_out, t_ends_out);
+      keep_head, head_cnt, head_base, head_t0, head_t1, keep_tail, tail_offsets, tail_t0, tail_t1, new_offsets, n_rays,
+      capacity > 0 ? capacity : INT64_MAX, ray_idx_out, t_starts_out, t_ends_out);
   return angio::finish_launch("angio_compact_head_tail");
 }
 

@@ -288,8 +288,9 @@ def alphas_two_phase(desc, params, packed, precision, rays_o, rays_d, ray_idx, t
 
 
 def march_head(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane, step_size, k0=32, pool=None):
-    """First k0 (<= 32) samples of every ray in ONE marching pass, ray-strided (sample j of ray r at r * k0 + j): returns
-    (head_t0, head_t1, head_cnt, t_resume, t_max).  Depends on the occupancy grid only, not on the model."""
+    """First k0 (<= 32) samples of every ray in ONE marching pass, packed without a scan (ray r: head_cnt[r] samples from slot
+    head_base[r]; the order of the rays in memory is unspecified): returns (head_idx, head_t0, head_t1, head_cnt, head_base,
+    head_total, t_resume, t_max).  Depends on the occupancy grid only, not on the model."""
     lib = _lib.load()
     if not 1 <= k0 <= 32:
         raise ValueError("k0 must be in 1..32")
@@ -299,23 +300,26 @@ def march_head(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_pl
     aabb = _host6(scene_aabb, "scene_aabb")
     roi = _host6(roi_aabb, "roi_aabb")
     R, dev = rays_o.shape[0], rays_o.device
+    h_idx = _alloc(pool, "lz_h_idx", R * k0, torch.int32, dev)
     h_t0 = _alloc(pool, "lz_h_t0", R * k0, torch.float32, dev)
     h_t1 = _alloc(pool, "lz_h_t1", R * k0, torch.float32, dev)
     h_cnt = torch.empty((R,), dtype=torch.int32, device=dev)
+    h_base = torch.empty((R,), dtype=torch.int32, device=dev)
+    h_total = torch.zeros((1,), dtype=torch.int32, device=dev)
     t_res = torch.empty((R,), dtype=torch.float32, device=dev)
     t_max = torch.empty((R,), dtype=torch.float32, device=dev)
     _lib.check(lib.angio_march_head(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
-                                    float(near_plane), float(far_plane), float(step_size), int(k0), _p(h_t0), _p(h_t1), _p(h_cnt), _p(t_res),
-                                    _p(t_max), _stream()), "angio_march_head")
-    return h_t0, h_t1, h_cnt, t_res, t_max
+                                    float(near_plane), float(far_plane), float(step_size), int(k0), _p(h_idx), _p(h_t0), _p(h_t1), _p(h_cnt),
+                                    _p(h_base), _p(h_total), _p(t_res), _p(t_max), _stream()), "angio_march_head")
+    return h_idx, h_t0, h_t1, h_cnt, h_base, h_total, t_res, t_max
 
 
 def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane,
                       step_size, early_stop_eps, alpha_thre, k0=32, totals=None, pool=None, timing=None, head=None):
     """acc_ray_marching (march -> alpha_fn -> visibility filter -> compaction) with LAZY marching and no host sync:
 
-      head   the first k0 samples of every ray, one marching pass into a ray-strided layout (no count / scan), alpha by the MLP
-             straight from that layout, visibility of the head, and which rays are still alive behind it;
+      head   the first k0 samples of every ray, one marching pass (no count / scan: warps reserve their slots atomically),
+             alpha, visibility of the head, and which rays are still alive behind it;
       tail   only for those rays: count -> scan -> write from where the head stopped, alpha, visibility continuing the head's
              transmittance;
       then   one scan of the kept counts and one compaction of head + tail into the packed layout.
@@ -341,7 +345,7 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
     # ---- head
     if head is None:
         head = march_head(rays_o, rays_d, aabb, roi, resolution, binary, near_plane, far_plane, step_size, k0=k0, pool=pool)
-    h_t0, h_t1, h_cnt, t_res, t_max = head
+    h_idx, h_t0, h_t1, h_cnt, h_base, h_total, t_res, t_max = head
     if h_t0.numel() < R * k0 or h_cnt.numel() != R:
         raise ValueError("march_filter_lazy: `head` does not belong to these rays / this k0")
     h_alpha = _alloc(pool, "lz_h_alpha", R * k0, f32, dev)
@@ -349,25 +353,25 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
     h_kept = torch.empty((R,), dtype=i32, device=dev)
     t_end = torch.empty((R,), dtype=f32, device=dev)
     alive = torch.empty((R,), dtype=u8, device=dev)
-    marched = torch.zeros((2,), dtype=i32, device=dev)                       # [head samples, tail samples]
+    tail_total = torch.zeros((1,), dtype=i32, device=dev)
     if timing is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    s = Samples(R * k0, None, _p(rays_o), _p(rays_d), None, _p(h_t0), _p(h_t1), None, _p(h_cnt), int(k0), None)
+    s = Samples(R * k0, None, _p(rays_o), _p(rays_d), _p(h_idx), _p(h_t0), _p(h_t1), None, _p(h_total))
     _lib.check(lib.angio_mlp_forward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), OUT_ALPHA, PREC_BF16, _p(h_alpha), None,
                                      None, 0, _stream()), "angio_mlp_forward")
     if timing is not None:
         ev1.record()
-        timing.append((ev0, ev1, marched[0:1]))
-    _lib.check(lib.angio_visibility_head_mask(_p(h_alpha), _p(h_cnt), R, int(k0), float(early_stop_eps), float(alpha_thre), _p(h_keep),
-                                              _p(h_kept), _p(t_end), _p(alive), _p(marched), _stream()), "angio_visibility_head_mask")
+        timing.append((ev0, ev1, h_total))
+    _lib.check(lib.angio_visibility_head_mask(_p(h_alpha), _p(h_cnt), _p(h_base), R, int(k0), float(early_stop_eps), float(alpha_thre),
+                                              _p(h_keep), _p(h_kept), _p(t_end), _p(alive), _stream()), "angio_visibility_head_mask")
     # ---- tail of the rays that are still alive (usually few; the kernels do nothing for the others)
     counts = torch.empty((R,), dtype=i32, device=dev)
     runs = _alloc(pool, "lz_runs", int(lib.angio_march_runs_bytes(R)), u8, dev)
     _lib.check(lib.angio_march_count(_p(rays_o), _p(rays_d), R, aabb.ctypes.data, roi.ctypes.data, int(resolution), _p(binary),
                                      float(near_plane), float(far_plane), float(step_size), _p(t_res), _p(t_max), _p(counts), _p(runs),
                                      _p(alive), _stream()), "angio_march_count")
-    t_off = exclusive_scan(counts, marched[1:2])
+    t_off = exclusive_scan(counts, tail_total)
     t_idx = _alloc(pool, "lz_t_idx", cap, i32, dev)
     t_t0 = _alloc(pool, "lz_t_t0", cap, f32, dev)
     t_t1 = _alloc(pool, "lz_t_t1", cap, f32, dev)
@@ -378,12 +382,12 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
     if timing is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    s = Samples(cap, None, _p(rays_o), _p(rays_d), _p(t_idx), _p(t_t0), _p(t_t1), None, None, 0, _p(t_off[R:R + 1]))
+    s = Samples(cap, None, _p(rays_o), _p(rays_d), _p(t_idx), _p(t_t0), _p(t_t1), None, _p(t_off[R:R + 1]))
     _lib.check(lib.angio_mlp_forward(ctypes.byref(desc), _p(params), _p(packed), ctypes.byref(s), OUT_ALPHA, PREC_BF16, _p(t_alpha), None,
                                      None, 0, _stream()), "angio_mlp_forward")
     if timing is not None:
         ev1.record()
-        timing.append((ev0, ev1, marched[1:2]))
+        timing.append((ev0, ev1, tail_total))
     kept = torch.empty((R,), dtype=i32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(t_alpha), _p(t_off), R, float(early_stop_eps), float(alpha_thre), _p(t_keep), _p(kept), _p(t_end),
                                          _p(h_kept), _stream()), "angio_visibility_mask")
@@ -392,10 +396,10 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
     ray_idx = _alloc(pool, "kept_idx", cap, i32, dev)
     t0 = _alloc(pool, "kept_t0", cap, f32, dev)
     t1 = _alloc(pool, "kept_t1", cap, f32, dev)
-    _lib.check(lib.angio_compact_head_tail(_p(h_keep), _p(h_cnt), _p(h_t0), _p(h_t1), int(k0), _p(t_keep), _p(t_off), _p(t_t0), _p(t_t1),
+    _lib.check(lib.angio_compact_head_tail(_p(h_keep), _p(h_cnt), _p(h_base), _p(h_t0), _p(h_t1), _p(t_keep), _p(t_off), _p(t_t0), _p(t_t1),
                                            _p(new_off), R, cap, _p(ray_idx), _p(t0), _p(t1), _stream()), "angio_compact_head_tail")
     if totals is not None:
-        torch.add(marched[0:1], marched[1:2], out=totals[0:1])
+        torch.add(h_total, tail_total, out=totals[0:1])
     return ray_idx, t0, t1, new_off
 
 
@@ -483,7 +487,7 @@ def _samples(points=None, rays_o=None, rays_d=None, ray_idx=None, t_starts=None,
     sample_idx = _chk(sample_idx, torch.int32, "sample_idx", 1, allow_none=True)
     if sample_idx is not None:
         n = sample_idx.numel()
-    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(sample_idx), None, 0, _p(n_dev))
+    s = Samples(n, _p(points), _p(rays_o), _p(rays_d), _p(ray_idx), _p(t_starts), _p(t_ends), _p(sample_idx), _p(n_dev))
     return s, n
 
 
