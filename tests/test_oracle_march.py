@@ -123,3 +123,52 @@ def test_grid_update_semantics():
     before = g.occs.copy()
     g.every_n_step(16, lambda x: np.zeros(len(x), np.float32), occ_thre=1e-2, rng=rng)
     assert np.all(g.occs <= before) and np.all(g.occs >= before * np.float32(0.95) - 1e-9)     # EMA decay of touched cells
+
+
+def test_march_resumes_from_the_end_of_any_sample():
+    """The property lazy marching rests on: after emitting a sample the marcher's state is a function of
+    that sample's t_end alone, so marching a ray again with t_min = t_end of its k-th sample reproduces samples k+1 ... bit
+    for bit -- head (first k0 samples) + tail (resumed) = the full march.  Checked on the oracle for sparse and dense grids."""
+    rng = np.random.default_rng(5)
+    for fill, k0 in ((0.15, 32), (0.5, 7), (1.0, 32), (0.03, 1)):
+        g = nerfacc_ref.OccupancyGrid(ROI, 32)
+        g.binary[:] = rng.random(g.binary.shape) < fill
+        o, d = _rays(theta=40.0, phi=25.0, W=12)
+        t_min, t_max = nerfacc_ref.ray_aabb_intersect(o, d, ROI, 1400.0, 1600.0)
+        step = np.float32(200.0 / 300)
+        ri, ts, te, off = nerfacc_ref.march(o, d, t_min, t_max, ROI, 32, g.binary, step)
+        cnt = np.diff(off)
+        long_rays = np.nonzero(cnt > k0)[0]
+        assert len(long_rays) > 10
+        t_resume = t_min.copy()
+        t_resume[long_rays] = te[off[long_rays] + k0 - 1]
+        sel = long_rays
+        ri2, ts2, te2, off2 = nerfacc_ref.march(o[sel], d[sel], t_resume[sel], t_max[sel], ROI, 32, g.binary, step)
+        assert np.array_equal(np.diff(off2), cnt[sel] - k0)
+        tail = np.concatenate([np.arange(off[r] + k0, off[r + 1]) for r in sel])
+        assert np.array_equal(ts2, ts[tail]) and np.array_equal(te2, te[tail])
+
+
+def test_visibility_of_head_plus_tail_equals_full_filter():
+    """Second half of the lazy-marching argument: filtering the first k0 samples of every ray, carrying the transmittance
+    over and filtering the rest only for rays that are still >= early_stop_eps keeps exactly the samples the reference's
+    filter keeps on the full ray (alpha in [0, 1]: the transmittance never recovers)."""
+    rng = np.random.default_rng(11)
+    R, k0, eps, thre = 200, 32, np.float32(1e-2), np.float32(1e-3)
+    cnt = rng.integers(0, 120, R)
+    off = np.zeros(R + 1, np.int64); np.cumsum(cnt, out=off[1:])
+    alphas = (rng.random(off[-1]) ** 3).astype(np.float32) * np.float32(0.4)
+    alphas[rng.random(off[-1]) < 0.1] = 0.0
+    full = nerfacc_ref.visibility(off, alphas, eps, thre)
+    keep = np.zeros_like(full)
+    for r in range(R):
+        a = alphas[off[r]:off[r + 1]]
+        T = np.float32(1.0)
+        for j in range(min(k0, len(a))):                      # head
+            keep[off[r] + j] = (T >= eps) and (a[j] >= thre)
+            T = np.float32(T * np.float32(np.float32(1.0) - a[j]))
+        if len(a) > k0 and T >= eps:                          # tail: only if the ray is still transparent behind its head
+            for j in range(k0, len(a)):
+                keep[off[r] + j] = (T >= eps) and (a[j] >= thre)
+                T = np.float32(T * np.float32(np.float32(1.0) - a[j]))
+    assert np.array_equal(keep, full)
