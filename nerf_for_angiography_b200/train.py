@@ -341,6 +341,14 @@ class Trainer:
                                   if id(self.ray_gen) in self.pool._seed_streams else None)))
         self.model.save(filename, info)
 
+    def save_grids(self, log_dir, prefix="coarse"):
+        """`pv_grid.save(f"{log_dir}coarsegrid.vtk")` / `...coarsevesselgrid.vtk` (run_nerf_acc.py:359-367; prefix 'high' at
+        :384-385): the occupancy grids in the reference's legacy-VTK layout, readable by its inference script."""
+        from . import gridio
+        gridio.save_grid_vtk(os.path.join(log_dir, f"{prefix}grid.vtk"), self.acc_grid)
+        if self.vessel_acc_grid is not None:
+            gridio.save_grid_vtk(os.path.join(log_dir, f"{prefix}vesselgrid.vtk"), self.vessel_acc_grid)
+
     def load_checkpoint(self, filename):
         """Restore model + optimiser + grids + counters from save_checkpoint (or just the model from a reference .pth)."""
         ck = torch.load(filename, map_location="cpu", weights_only=False)
