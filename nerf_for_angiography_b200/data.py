@@ -52,6 +52,53 @@ def rev_sigmoid(x, c1=1.0, c2=0.0):
     return 1.0 / (1.0 + torch.exp(c1 * (x - c2)))
 
 
+# CT transfer function knots (HU -> attenuation) "used for ALL experiments" and its binary variant, /root/reference/phantomdata/helpers.py:33-70
+_TF_X = (0.0, 753.0, 1585.85, 2332.9, 3306.18, 4000.0)
+_TF_Y = (0.0, 0.0, 0.05, 0.0, 0.2, 0.4)
+_TF_Y_BINARY = (0.0, 0.0, 0.0, 0.0, 0.2, 0.4)
+
+
+def transfer_func_ct(vals, binary=False):
+    """Piecewise-linear HU -> attenuation map of the reference's CT phantoms (helpers.py:33-70): 0 below 0 HU, linear between
+    the knots (each segment evaluated as m*x + b with the reference's m and b, float64), 0.4 from 4000 HU on."""
+    v = np.asarray(vals).astype("float64")
+    ys = _TF_Y_BINARY if binary else _TF_Y
+    out = np.empty_like(v)
+    out[v < _TF_X[0]] = ys[0]
+    for k in range(5):
+        x1, x2, y1, y2 = _TF_X[k], _TF_X[k + 1], ys[k], ys[k + 1]
+        sel = (v >= x1) & (v < x2)
+        m = (y1 - y2) / (x1 - x2)
+        b = (x1 * y2 - x2 * y1) / (x1 - x2)
+        out[sel] = m * v[sel] + b
+    out[v >= _TF_X[5]] = ys[5]
+    return out
+
+
+def get_weighted_img(img, sampling_strategy="segmentation"):
+    """Sampling-weight image of one projection (helpers.py:226-247, the `distance_pixel_value` column): mask of the pixels
+    darker than 1 ('segmentation'; 'frangi' needs scikit-image), min-max normalised, Euclidean distance transform,
+    min-max normalised again, + 1e-10 so that every pixel can be drawn.  Host side (scipy), once per projection."""
+    from scipy.ndimage import distance_transform_edt
+    img = np.asarray(img)
+    if sampling_strategy == "frangi":
+        try:
+            from skimage.filters import frangi
+        except ImportError as e:
+            raise NotImplementedError("sampling_strategy='frangi' needs scikit-image, which is not installed") from e
+        mask = frangi(img, alpha=0.5, beta=0.5)
+    else:
+        mask = np.zeros(img.shape)
+        mask[img < 1] = 1
+    mask -= np.min(mask)
+    mask /= np.max(mask)
+    w = distance_transform_edt(mask)
+    w -= np.min(w)
+    w /= np.max(w)
+    w += 1e-10
+    return w
+
+
 def make_volume(resolution=256, half_extent=100.0, kind="sdf", device="cuda", seed=0):
     """Attenuation volume mu[res,res,res] (indexed [x,y,z]) on the +-half_extent lattice.
 
@@ -228,6 +275,8 @@ def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0,
         weights = None
     elif weight_strategy == "segmentation":                      # helpers.py:229-244 without the EDT: vessel pixels up-weighted
         weights = (pix < pix.flatten(1).mean(dim=1)[:, None, None]).float() + 1e-3
+    elif weight_strategy == "distance":                          # the reference's weight image (mask -> EDT), per projection on the host
+        weights = torch.stack([torch.from_numpy(get_weighted_img(p.cpu().numpy())).float() for p in pix]).to(device)
     else:
         raise ValueError(weight_strategy)
     info = dict(focal=focal, src_dist=src_dist, near=src_dist - half_extent, far=src_dist + half_extent, views=views,

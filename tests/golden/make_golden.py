@@ -139,6 +139,18 @@ def main():
                         t_ends=t_ends.numpy(), pred=pred.detach().numpy(), pix=pix.detach().numpy(), gpix=gp.numpy(),
                         gpred=pred.grad.numpy(), pix_zero=pix_zero.numpy(), zero_mask=(sig < 0.4).numpy(),
                         n_rays=np.array(n_rays), o=o.numpy(), d=d.numpy(), positions=positions.numpy())
+    # ---------------------------------------------------------------- phantom helpers (f2): transfer function + weight image
+    rng = np.random.default_rng(7)
+    hu = np.concatenate([rng.uniform(-500.0, 4500.0, 4000), np.array([0.0, 753.0, 1585.85, 2332.9, 3306.18, 4000.0, -1.0, 752.999, 3999.999])])
+    tf = phantom_helpers.transfer_func_ct(hu)
+    tf_bin = phantom_helpers.transfer_func_ct(hu, binary=True)
+    sys.modules["matplotlib.pyplot"].imsave = lambda *a, **k: None          # get_weighted_img also writes a png
+    img = np.ones((48, 40))
+    yy, xx = np.mgrid[0:48, 0:40]
+    img[(np.abs(xx - 12 - 0.3 * yy) < 2.5) | ((xx - 28) ** 2 + (yy - 30) ** 2 < 30)] = 0.35      # a vessel and a blob, pixel value < 1
+    img += rng.uniform(-0.05, 0.0, img.shape) * (img < 1)
+    wimg = phantom_helpers.get_weighted_img(img.copy(), 0.5, 0.5, 0, 0, 0, "/tmp/", sampling_strategy="segmentation")
+    np.savez_compressed(os.path.join(OUT, "phantom.npz"), hu=hu, tf=tf, tf_bin=tf_bin, img=img, wimg=wimg)
     print("golden vectors written to", OUT)
 
 
