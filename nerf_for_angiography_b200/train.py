@@ -388,11 +388,21 @@ class Trainer:
 
     @torch.no_grad()
     def evaluate(self, v=None):
-        """PSNR of the test view (the LAST view of the pool, run_nerf_acc.py:85)."""
+        """PSNR of the test view (the LAST view of the pool, run_nerf_acc.py:85,355-357) and, when the pool carries a
+        sampling-weight image, the vessel-pixel PSNR over the test-view pixels whose weight exceeds the view's mean weight
+        (run_nerf_acc.py:102-105,370-374; None when there is no such pixel or no weight image)."""
         v = self.pool.n_views - 1 if v is None else v
         pix, target = self.render_view(v)
         mse = torch.mean((pix - target) ** 2)
-        return dict(mse=float(mse), psnr=float(-10.0 * torch.log10(mse)), image=pix.view(self.pool.img_h, self.pool.img_w))
+        vessel_psnr = None
+        w = getattr(self.pool, "weights", None)
+        if w is not None:
+            wv = w[int(v)].reshape(-1)
+            sel = wv > wv.mean()
+            if bool(sel.any()):
+                vessel_psnr = float(-10.0 * torch.log10(torch.mean((pix[sel] - target[sel]) ** 2)))
+        return dict(mse=float(mse), psnr=float(-10.0 * torch.log10(mse)), vessel_psnr=vessel_psnr,
+                    image=pix.view(self.pool.img_h, self.pool.img_w))
 
 
 def psnr_from_loss(loss: float) -> float:

@@ -401,6 +401,18 @@ def test_sampler_edge_cases(A):
     assert pool.last_status.tolist()[1] == 1
 
 
+def test_sampler_with_the_reference_weight_images(A):
+    """make_dataset(weight_strategy='distance'): the reference's mask -> EDT weight images (background pixels weigh 1e-10,
+    helpers.py:226-247) through the sampler: the draw is complete, unique and lands on the weighted pixels."""
+    from nerf_for_angiography_b200.data import make_dataset
+    pool, _ = make_dataset(img_size=32, thetas=(0.0, 60.0, 120.0), kind="ct", volume_res=32, device="cuda", weight_strategy="distance")
+    w = pool.weights.reshape(-1)
+    assert float(w.min()) > 0 and abs(float(w.max()) - 1.0) < 1e-6 and int((w > 1e-6).sum()) > 600
+    ids = pool.sample_ids(512, generator=torch.Generator(device="cuda").manual_seed(3))
+    assert pool.last_status.tolist()[1] == 0 and ids.unique().numel() == 512
+    assert float((w[ids] > 1e-6).float().mean()) > 0.99
+
+
 def test_sampler_is_reproducible_and_shuffled(A):
     """Same seed -> the same ids in the same order (the candidate pass appends with atomics, the select/shuffle pass must
     erase that order); the order is a uniform shuffle (no correlation between position and ray id or weight)."""

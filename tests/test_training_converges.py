@@ -65,5 +65,12 @@ def test_gpu_training_loss_decreases(precision):
     losses = [float(tr.step()["loss"]) for _ in range(150)]
     assert np.isfinite(losses).all()
     assert np.mean(losses[-10:]) < 0.5 * np.mean(losses[:10]), (losses[:3], losses[-3:])
+    if precision == "bf16":                      # attach the reference's weight image (mask -> EDT) for the vessel-pixel PSNR
+        from nerf_for_angiography_b200.data import get_weighted_img
+        pool.weights = torch.stack([torch.from_numpy(get_weighted_img(p.cpu().numpy())).float() for p in pool.pixels]).to(dev)
     ev = tr.evaluate()
     assert ev["psnr"] > 12.0 and ev["image"].shape == (32, 32)
+    if precision == "bf16":
+        assert ev["vessel_psnr"] is not None and np.isfinite(ev["vessel_psnr"])       # pixels with weight > the view's mean weight
+    else:
+        assert ev["vessel_psnr"] is None
