@@ -142,13 +142,17 @@ class RayPool:
     (nerf/run_nerf_acc.py:113-117): a ray is the integer triple (view, x, y) and is expanded by the ray-generation
     kernel when sampled."""
 
-    def __init__(self, cam2world, pixels, focal, weights=None):
+    def __init__(self, cam2world, pixels, focal, weights=None, train_on_test_view=True):
         self.cam2world = cam2world.contiguous()                 # [V,4,4] float64, CUDA
         self.pixels = pixels.contiguous()                       # [V,H,W] float32
         self.focal = float(focal)
         self.n_views, self.img_h, self.img_w = pixels.shape
         self.weights = None if weights is None else weights.contiguous().float()
         self.n_rays = self.n_views * self.img_h * self.img_w
+        # The reference trains on the test view too (`train_ray_df = ray_df.copy()`, run_nerf_acc.py:114; the test view is the
+        # LAST one, :85).  train_on_test_view=False draws training rays from the other views only.
+        self.train_on_test_view = bool(train_on_test_view)
+        self.n_train_rays = self.n_rays if self.train_on_test_view else (self.n_views - 1) * self.img_h * self.img_w
         self._wsum = None
         self._seed_streams = {}
         self._bufs = ops.BufferPool()
@@ -168,12 +172,12 @@ class RayPool:
         """Weighted sampling without replacement of n ray ids (exponential-race / Efraimidis-Spirakis keys with a
         threshold pre-filter so only ~n + 8 sqrt(n) candidates reach the exact selection), then a random shuffle -- the
         reference's ``DataFrame.sample(n, weights).sample(frac=1)`` (nerf/nerf_helpers.py:139).  Two kernel launches, no sync."""
-        N, dev = self.n_rays, self.device
+        N, dev = self.n_train_rays, self.device
         if n > N:
             raise ValueError("cannot sample more rays than the pool holds without replacement")
         w = self.weights if weights is None else (None if isinstance(weights, str) and weights == "uniform" else weights)
         if w is not None:
-            wf = w.reshape(-1).contiguous().float()
+            wf = w.reshape(-1).contiguous().float()[:N]          # ray ids are view-major: a prefix = the training views
             if weights is not None and not isinstance(weights, str):
                 wsum, wsum2 = float(wf.sum().item()), float((wf.double() ** 2).sum().item())
             else:
@@ -253,7 +257,8 @@ class ExplicitRayPool:
 
 
 def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0, 135.0), kind="ct", volume_res=128,
-                 n_proj_samples=300, src_dist=1500.0, half_extent=100.0, device="cuda", seed=0, weight_strategy="random"):
+                 n_proj_samples=300, src_dist=1500.0, half_extent=100.0, device="cuda", seed=0, weight_strategy="random",
+                 train_on_test_view=True):
     """Views theta in `thetas` (phi = 0) + the test view (theta, phi) LAST (the reference treats the last projection
     as the test view and keeps it in the training pool, nerf/run_nerf_acc.py:85,114).  Focal length 7.5*W makes the
     detector span the AABB at the isocentre.  Returns (RayPool, info dict)."""
@@ -281,4 +286,4 @@ def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0,
         raise ValueError(weight_strategy)
     info = dict(focal=focal, src_dist=src_dist, near=src_dist - half_extent, far=src_dist + half_extent, views=views,
                 half_extent=half_extent, volume=vol)
-    return RayPool(cam, pix, focal, weights), info
+    return RayPool(cam, pix, focal, weights, train_on_test_view=train_on_test_view), info

@@ -413,6 +413,26 @@ def test_sampler_with_the_reference_weight_images(A):
     assert float((w[ids] > 1e-6).float().mean()) > 0.99
 
 
+def test_pool_can_exclude_the_test_view(A):
+    """The reference trains on the test view as well (run_nerf_acc.py:114) -- the default; train_on_test_view=False keeps the
+    last view out of the training draws (uniform and weighted)."""
+    from nerf_for_angiography_b200.data import RayPool
+    V, H, W = 3, 32, 48
+    cam = torch.eye(4, dtype=torch.float64, device="cuda").repeat(V, 1, 1)
+    w = torch.rand(V, H, W, device="cuda") + 0.1
+    w[-1] = 100.0                                                 # the test view would dominate a weighted draw
+    for weights in (None, w):
+        ref = RayPool(cam, torch.rand(V, H, W, device="cuda"), 100.0, weights)
+        ids = ref.sample_ids(2000, generator=torch.Generator(device="cuda").manual_seed(1))
+        assert int(ids.max()) >= (V - 1) * H * W                  # reference behaviour: test-view rays are drawn
+        pool = RayPool(cam, torch.rand(V, H, W, device="cuda"), 100.0, weights, train_on_test_view=False)
+        ids = pool.sample_ids(2000, generator=torch.Generator(device="cuda").manual_seed(1))
+        assert pool.last_status.tolist()[1] == 0 and ids.unique().numel() == 2000 and int(ids.max()) < (V - 1) * H * W
+        assert pool.rays_of_view(V - 1)[2].numel() == H * W       # the test view itself stays available for evaluation
+    with pytest.raises(ValueError):
+        pool.sample_ids((V - 1) * H * W + 1)
+
+
 def test_sampler_is_reproducible_and_shuffled(A):
     """Same seed -> the same ids in the same order (the candidate pass appends with atomics, the select/shuffle pass must
     erase that order); the order is a uniform shuffle (no correlation between position and ray id or weight)."""
