@@ -73,3 +73,25 @@ def test_python_surface_fails_loudly_on_cpu_tensors():
     from nerf_for_angiography_b200 import ops
     with pytest.raises(ValueError):
         ops.composite_forward(torch.zeros(4), torch.zeros(4), torch.ones(4), torch.tensor([0, 4], dtype=torch.int32))
+
+
+def test_buffer_pool_is_grow_only_and_stable():
+    """Host logic of the scratch pool behind the sync-free loop: a request that fits returns the SAME storage (no allocation in
+    steady state), growth doubles, reserve() is exact, typed() carves dtype views."""
+    import torch
+    from nerf_for_angiography_b200.ops import BufferPool
+    cpu = torch.device("cpu")
+    pool = BufferPool()
+    a = pool.get("x", 1000, cpu)
+    assert a.dtype == torch.uint8 and a.numel() >= 2000
+    assert pool.get("x", 1500, cpu).data_ptr() == a.data_ptr()            # fits: same block
+    b = pool.get("x", 5000, cpu)
+    assert b.numel() >= 10000                                             # grew by doubling the request
+    assert pool.get("x", 10, cpu).data_ptr() == b.data_ptr()              # never shrinks
+    r = pool.reserve("saved", 4096, cpu)
+    assert 4096 <= r.numel() <= 4096 + 256 and pool.reserve("saved", 100, cpu).data_ptr() == r.data_ptr()
+    t = pool.typed("ids", 100, torch.int32, cpu)
+    assert t.dtype == torch.int32 and t.numel() == 100
+    t[:] = 7
+    assert pool.typed("ids", 50, torch.int32, cpu).data_ptr() == t.data_ptr() and int(pool.typed("ids", 50, torch.int32, cpu)[49]) == 7
+    assert pool.typed("f", 3, torch.float32, cpu).dtype == torch.float32
