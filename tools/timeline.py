@@ -2,6 +2,7 @@
 idle gap before it, plus the busy fraction of the step.  Diagnostic only -- not a bench number.
 
     python tools/timeline.py [--workload config3] [--steps 2] [--start-iter 257]
+    python tools/timeline.py --train-steps 70 --start-iter -1 --steps 2 --merge     # per-kernel totals after 70 real iterations
 """
 import argparse
 import os
