@@ -127,16 +127,19 @@ ANGIO_API int angio_grid_query(const float* points, int64_t n, const float* roi_
  * (alpha_thre <= 0 or alpha_i >= alpha_thre).
  */
 /* t_init (optional, [n_rays]): transmittance each ray starts with (tail of a lazily marched ray; NULL = 1);
- * base_counts (optional): added to kept_counts (the kept head samples). */
+ * base_counts (optional): added to kept_counts (the kept head samples);
+ * alpha_thre_cap (optional, DEVICE float): the threshold used is min(alpha_thre, *alpha_thre_cap) -- nerfacc.ray_marching
+ * clamps alpha_thre to mean(grid.occs); passing the device-resident mean keeps the training loop free of host syncs. */
 ANGIO_API int angio_visibility_mask(const float* alphas, const int32_t* offsets, int64_t n_rays,
                           float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts,
-                          const float* t_init, const int32_t* base_counts, void* stream);
+                          const float* t_init, const int32_t* base_counts, const float* alpha_thre_cap, void* stream);
 /* Visibility of the head samples of angio_march_head: keep flags (indexed like the head arrays), kept count, transmittance
  * behind the head (t_end) and alive[r] = the head used its whole budget and t_end >= early_stop_eps (the ray must be
  * continued). */
 ANGIO_API int angio_visibility_head_mask(const float* alphas, const int32_t* head_cnt, const int32_t* head_base,
                                int64_t n_rays, int32_t k0, float early_stop_eps, float alpha_thre, uint8_t* keep,
-                               int32_t* kept_counts, float* t_end, uint8_t* alive, void* stream);
+                               int32_t* kept_counts, float* t_end, uint8_t* alive, const float* alpha_thre_cap,
+                               void* stream);
 /* Compaction of a lazily marched batch into the packed layout: per ray the kept head samples, then the kept tail samples. */
 ANGIO_API int angio_compact_head_tail(const uint8_t* keep_head, const int32_t* head_cnt, const int32_t* head_base,
                             const float* head_t0, const float* head_t1, const uint8_t* keep_tail,
@@ -288,12 +291,15 @@ ANGIO_API int angio_project_volume(const float* volume, int32_t nx, int32_t ny, 
  * sums the `world` gradient buffers (peer_grads_host[r]: device address of rank r's gradient as mapped here) in rank order --
  * bit-identical on every rank -- and applies angio_adam_step's update in the same pass.  active_index >= 0 names a gradient
  * slot whose all-rank sum gates the step (0 = skip), < 0 disables the gate.  Callers alternate two gradient buffers by step
- * parity.  Replaces the NCCL all_reduce + Adam pair; the pointer arrays are HOST arrays of `world` (<= 16) entries. */
+ * parity.  Replaces the NCCL all_reduce + Adam pair; the pointer arrays are HOST arrays of `world` (<= 16) entries.
+ * wait_stats (optional, DEVICE uint64[4]): block 0 accumulates [nanoseconds spent waiting for the peers' tags (globaltimer),
+ * number of calls, longest single wait, 0] -- the measurement of how long a rank stalls on its slowest peer.  A peer that
+ * does not signal within ANGIO_PEER_TIMEOUT_S seconds (environment, default 600) traps the kernel. */
 ANGIO_API int angio_signal_peers(void* const* peer_flags_host, int32_t world, int32_t rank, uint32_t tag, void* stream);
 ANGIO_API int angio_adam_step_allreduce(float* params, const void* const* peer_grads_host, int32_t world,
                               const uint32_t* my_flags, uint32_t tag, float* exp_avg, float* exp_avg_sq, int64_t n,
                               float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
-                              int64_t active_index, void* stream);
+                              int64_t active_index, unsigned long long* wait_stats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -43,8 +43,8 @@ PROTOTYPES = {
     "angio_exclusive_scan_i32": (c_i32, [c_ptr, c_i64, c_ptr, c_ptr, c_ptr]),
     "angio_march_write": (c_i32, [c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_grid_query": (c_i32, [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
-    "angio_visibility_mask": (c_i32, [c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "angio_visibility_head_mask": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_visibility_mask": (c_i32, [c_ptr, c_ptr, c_i64, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "angio_visibility_head_mask": (c_i32, [c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_f32, c_f32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_compact_head_tail": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_counts": (c_i32, [c_ptr, c_i64, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "angio_ray_segment_ids": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_ptr, c_ptr]),
@@ -67,7 +67,7 @@ PROTOTYPES = {
     "angio_project_volume": (c_i32, [c_ptr, c_i32, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr]),
     "angio_signal_peers": (c_i32, [c_ptr, c_i32, c_i32, ctypes.c_uint32, c_ptr]),
     "angio_adam_step_allreduce": (c_i32, [c_ptr, c_ptr, c_i32, c_ptr, ctypes.c_uint32, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32,
-                                          c_f32, c_i64, c_ptr]),
+                                          c_f32, c_i64, c_ptr, c_ptr]),
     "angio_adam_step": (c_i32, [c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_f32, c_f32, c_f32, c_f32, c_i32, c_f32, c_ptr, c_ptr]),
 }
 

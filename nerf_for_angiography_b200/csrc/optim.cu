@@ -2,6 +2,8 @@
 // Replaces torch.optim.Adam(lr=1e-4).step() (/root/reference/nerf/run_nerf_acc.py:206,305-307) with the same
 // update formula torch uses (bias corrections folded the same way), one HBM-bound pass: 16 B/param read,
 // 12 B/param written.  grad_scale folds the 1/world_size of the data-parallel gradient mean.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -39,6 +41,11 @@ __global__ void signal_peers_kernel(PeerFlags peers, int world, int rank, uint32
   }
 }
 
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -48,15 +55,24 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(float* __restrict__ p, PeerPtrs peers, int world, const uint32_t* my_flags,
                                                              uint32_t tag, float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                              float lr, float b1, float b2, float eps, float step_size, float bc2_sqrt,
-                                                             float gscale, int64_t active_index) {
+                                                             float gscale, int64_t active_index, unsigned long long timeout_ns,
+                                                             unsigned long long* __restrict__ wait_stats) {
   __shared__ float s_active;
   if (threadIdx.x == 0) {
+    const unsigned long long t_start = global_timer_ns();
     for (int r = 0; r < world; ++r) {
       unsigned spins = 0;
       while ((int32_t)(ld_acquire_sys(my_flags + r) - tag) < 0) {      // wrap-safe "flag >= tag"
-        if (++spins > (1u << 28)) __trap();                             // a peer died: fail loudly instead of hanging
+        // a peer died: fail loudly instead of hanging (wall-clock bound: rank 0 may legitimately be busy with an evaluation)
+        if ((++spins & 1023u) == 0 && global_timer_ns() - t_start > timeout_ns) __trap();
         __nanosleep(64);
       }
+    }
+    if (wait_stats && blockIdx.x == 0) {          // how long this rank stalled on its slowest peer (bench.py: allreduce_wait_us)
+      const unsigned long long w = global_timer_ns() - t_start;
+      wait_stats[0] += w;
+      wait_stats[1] += 1ull;
+      if (w > wait_stats[2]) wait_stats[2] = w;
     }
     float a = 1.0f;
     if (active_index >= 0) {
@@ -91,7 +107,8 @@ extern "C" int angio_signal_peers(void* const* peer_flags_host, int32_t world, i
 
 extern "C" int angio_adam_step_allreduce(float* params, const void* const* peer_grads_host, int32_t world, const uint32_t* my_flags,
                                          uint32_t tag, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
-                                         float eps, int32_t step, float grad_scale, int64_t active_index, void* stream) {
+                                         float eps, int32_t step, float grad_scale, int64_t active_index, unsigned long long* wait_stats,
+                                         void* stream) {
   ANGIO_REQUIRE(params && peer_grads_host && my_flags && exp_avg && exp_avg_sq && n >= 0 && step >= 1 && world >= 1 && world <= kMaxPeers,
                 "angio_adam_step_allreduce: bad arguments");
   if (n == 0) return 0;
@@ -99,11 +116,16 @@ extern "C" int angio_adam_step_allreduce(float* params, const void* const* peer_
   for (int r = 0; r < world; ++r) pp.grad[r] = reinterpret_cast<const float*>(peer_grads_host[r]);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  static const unsigned long long timeout_ns = [] {
+    const char* e = getenv("ANGIO_PEER_TIMEOUT_S");
+    const double s = e ? atof(e) : 600.0;
+    return (unsigned long long)((s > 0.0 ? s : 600.0) * 1e9);
+  }();
   int blocks = angio::blocks_for(n, 256);
   const int cap = angio::sm_count() * 8;
   angio::note_launch(); adam_allreduce_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(
       params, pp, world, my_flags, tag, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)((double)lr / bc1), (float)sqrt(bc2), grad_scale,
-      active_index);
+      active_index, timeout_ns, wait_stats);
   return angio::finish_launch("angio_adam_step_allreduce");
 }
 

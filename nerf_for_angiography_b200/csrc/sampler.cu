@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(kSelThreads) radix_hist_kernel(const float* __
 
 // one CTA: the three bins -> threshold bit pattern + ties to take; also the status words of the call
 __global__ void __launch_bounds__(kSelThreads) select_finish_kernel(int32_t* __restrict__ ctl, int32_t capacity, int32_t n,
-                                                                   const uint32_t* __restrict__ hists, int32_t* __restrict__ status) {
+                                                                   const uint32_t* __restrict__ hists, int32_t* __restrict__ status,
+                                                                   int64_t* __restrict__ ids_out) {
   __shared__ uint32_t s_scan[32];
   __shared__ uint32_t s_out[2];
   const int count = ctl[0];
@@ -155,7 +156,12 @@ __global__ void __launch_bounds__(kSelThreads) select_finish_kernel(int32_t* __r
     status[0] = count;
     status[1] = (count > capacity || m < n) ? 1 : 0;        // overflow / too few candidates: the caller re-draws with a larger tau
   }
-  if (m < n) return;
+  if (m < n) {
+    // failed draw (fewer candidates than requested): the later kernels return early, so leave VALID ids behind (ray 0) --
+    // the gather that follows dereferences them before any host code has looked at status[1]
+    for (int i = threadIdx.x; i < n; i += kSelThreads) ids_out[i] = 0;
+    return;
+  }
   uint32_t prefix = 0, need = (uint32_t)n;
   for (int pass = 0; pass < 3; ++pass) {
     find_bin(hists + hist_off(pass), 1 << hist_bits(pass), need, s_scan, s_out);
@@ -354,7 +360,7 @@ extern "C" int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n
   angio::note_launch(); radix_hist_kernel<0><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
   angio::note_launch(); radix_hist_kernel<1><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
   angio::note_launch(); radix_hist_kernel<2><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch(); select_finish_kernel<<<1, kSelThreads, 0, st>>>(ctl, capacity, (int32_t)n, hists, status);
+  angio::note_launch(); select_finish_kernel<<<1, kSelThreads, 0, st>>>(ctl, capacity, (int32_t)n, hists, status, ids_out);
   angio::note_launch(); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, seed, log2b, bcount);
   angio::note_launch(); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, n_buckets, log2b, bcount, bfill,
                                                                           bstart, tmp_hash, tmp_ids);

@@ -16,8 +16,9 @@ __global__ void __launch_bounds__(256) visibility_mask_kernel(const float* __res
                                                               const int32_t* __restrict__ offsets, int64_t n_rays,
                                                               float eps, float thre, uint8_t* __restrict__ keep,
                                                               int32_t* __restrict__ kept_counts, const float* __restrict__ t_init,
-                                                              const int32_t* __restrict__ base_counts) {
+                                                              const int32_t* __restrict__ base_counts, const float* __restrict__ thre_cap) {
   const int lane = threadIdx.x % 32;
+  if (thre_cap) thre = fminf(thre, *thre_cap);    // nerfacc: alpha_thre = min(alpha_thre, mean(grid.occs)), the mean stays on the device
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
   for (int64_t r = warp_global; r < n_rays; r += n_warps) {
@@ -89,8 +90,10 @@ __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict_
 __global__ void __launch_bounds__(256) visibility_head_mask_kernel(const float* __restrict__ alphas, const int32_t* __restrict__ head_cnt,
                                                                    const int32_t* __restrict__ head_base, int64_t n_rays, int k0, float eps,
                                                                    float thre, uint8_t* __restrict__ keep, int32_t* __restrict__ kept_counts,
-                                                                   float* __restrict__ t_end, uint8_t* __restrict__ alive) {
+                                                                   float* __restrict__ t_end, uint8_t* __restrict__ alive,
+                                                                   const float* __restrict__ thre_cap) {
   const int lane = threadIdx.x % 32;
+  if (thre_cap) thre = fminf(thre, *thre_cap);
   const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
   const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
   for (int64_t r = warp_global; r < n_rays; r += n_warps) {
@@ -214,11 +217,11 @@ int warp_grid(int64_t n_rays) {
 
 extern "C" int angio_visibility_mask(const float* alphas, const int32_t* offsets, int64_t n_rays, float early_stop_eps,
                                      float alpha_thre, uint8_t* keep, int32_t* kept_counts, const float* t_init,
-                                     const int32_t* base_counts, void* stream) {
+                                     const int32_t* base_counts, const float* alpha_thre_cap, void* stream) {
   ANGIO_REQUIRE(offsets && kept_counts && n_rays >= 0, "angio_visibility_mask: bad arguments");
   if (n_rays == 0) return 0;
   angio::note_launch(); visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
-                                                                                 alpha_thre, keep, kept_counts, t_init, base_counts);
+                                                                                 alpha_thre, keep, kept_counts, t_init, base_counts, alpha_thre_cap);
   return angio::finish_launch("angio_visibility_mask");
 }
 
@@ -248,12 +251,12 @@ extern "C" int angio_visibility_head(const float* alphas, const int32_t* offsets
 
 extern "C" int angio_visibility_head_mask(const float* alphas, const int32_t* head_cnt, const int32_t* head_base, int64_t n_rays, int32_t k0,
                                           float early_stop_eps, float alpha_thre, uint8_t* keep, int32_t* kept_counts, float* t_end,
-                                          uint8_t* alive, void* stream) {
+                                          uint8_t* alive, const float* alpha_thre_cap, void* stream) {
   ANGIO_REQUIRE(alphas && head_cnt && head_base && keep && kept_counts && t_end && alive && n_rays >= 0 && k0 >= 1 && k0 <= 32,
                 "angio_visibility_head_mask: bad arguments");
   if (n_rays == 0) return 0;
   angio::note_launch(); visibility_head_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
-      alphas, head_cnt, head_base, n_rays, k0, early_stop_eps, alpha_thre, keep, kept_counts, t_end, alive);
+      alphas, head_cnt, head_base, n_rays, k0, early_stop_eps, alpha_thre, keep, kept_counts, t_end, alive, alpha_thre_cap);
   return angio::finish_launch("angio_visibility_head_mask");
 }
 

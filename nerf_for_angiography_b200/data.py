@@ -179,11 +179,13 @@ class RayPool:
         if w is not None:
             wf = w.reshape(-1).contiguous().float()[:N]          # ray ids are view-major: a prefix = the training views
             if weights is not None and not isinstance(weights, str):
-                wsum, wsum2 = float(wf.sum().item()), float((wf.double() ** 2).sum().item())
+                wsum, wsum2, npos = float(wf.sum().item()), float((wf.double() ** 2).sum().item()), int((wf > 0).sum().item())
             else:
-                if self._wsum is None:
-                    self._wsum = (float(wf.sum().item()), float((wf.double() ** 2).sum().item()))
-                wsum, wsum2 = self._wsum
+                if self._wsum is None:                           # one-off reductions when the weight image is first used
+                    self._wsum = (float(wf.sum().item()), float((wf.double() ** 2).sum().item()), int((wf > 0).sum().item()))
+                wsum, wsum2, npos = self._wsum
+            if n > npos:     # numpy / pandas: "Fewer non-zero entries in p than size" -- the draw could never be filled
+                raise ValueError(f"cannot sample {n} rays without replacement: only {npos} rays have a positive weight")
         else:
             wf, wsum, wsum2 = None, float(N), float(N)
         # per-call 62-bit seed from a host-side stream tied to the torch generator's seed: reproducible, rank-dependent,
@@ -244,8 +246,10 @@ class ExplicitRayPool:
         if weights is not None:
             wf = self.weight_columns[weights]
             if weights not in self._wsum:
-                self._wsum[weights] = (float(wf.sum().item()), float((wf.double() ** 2).sum().item()))
-            wsum, wsum2 = self._wsum[weights]
+                self._wsum[weights] = (float(wf.sum().item()), float((wf.double() ** 2).sum().item()), int((wf > 0).sum().item()))
+            wsum, wsum2, npos = self._wsum[weights]
+            if n > npos:
+                raise ValueError(f"cannot sample {n} rays without replacement: only {npos} rays have a positive weight")
         key = id(generator) if generator is not None else None
         rng = self._seed_streams.get(key)
         if rng is None:

@@ -77,6 +77,8 @@ class PeerGradients:
         self.peer_grad_ptrs = [arr(*[b + 4 * k * self.n_alloc for b in base]) for k in range(2)]
         self.peer_flag_ptrs = arr(*[b + 4 * 2 * self.n_alloc for b in base])
         self.tag = 0
+        # [ns spent waiting for peer tags, calls, longest wait, -] accumulated by the fused all-reduce + Adam kernel
+        self.wait_stats = torch.zeros(4, dtype=torch.int64, device=device)
         torch.cuda.synchronize(device)
         dist.barrier(group)                       # every rank's buffer is zeroed before anyone signals
 

@@ -43,7 +43,34 @@ class OccupancyGrid(torch.nn.Module):
         self.register_buffer("occs", torch.zeros(self.num_cells, dtype=torch.float32))
         self.register_buffer("_binary", torch.zeros((self._resolution,) * 3, dtype=torch.bool))
         self._roi_host = roi.cpu().numpy().copy()
-        self.occs_mean_host = 0.0   # host copy of mean(occs), refreshed by _update (read by ray_marching)
+        # mean(occs) caps alpha_thre in nerfacc.ray_marching.  It lives on the device (the visibility kernels read it there, so a
+        # training step never waits for it) and is tied to occs._version: occs restored through load_state_dict / copy_ / fill_
+        # invalidates it, and the next reader recomputes it (the kernels of _update write through raw pointers and record the
+        # version themselves).
+        self.register_buffer("_occs_mean", torch.zeros(1, dtype=torch.float32), persistent=False)
+        self._mean_version = None
+        self._mean_host = None
+
+    def occs_mean_dev(self):
+        """float32[1] device tensor holding mean(occs) (no host synchronisation)."""
+        if self._mean_version != self.occs._version:
+            torch.mean(self.occs, dim=0, keepdim=True, out=self._occs_mean)
+            self._mean_version, self._mean_host = self.occs._version, None
+        return self._occs_mean
+
+    @property
+    def occs_mean_host(self):
+        """mean(occs) as a python float (one device read when it is not cached) -- nerfacc evaluates `grid.occs.mean().item()`
+        on every ray_marching call."""
+        m = self.occs_mean_dev()
+        if self._mean_host is None:
+            self._mean_host = float(m.item())
+        return self._mean_host
+
+    @occs_mean_host.setter
+    def occs_mean_host(self, value):
+        self._occs_mean.fill_(float(value))
+        self._mean_version, self._mean_host = self.occs._version, float(value)
 
     # nerfacc properties
     @property
@@ -100,7 +127,8 @@ class OccupancyGrid(torch.nn.Module):
         occ = occ.reshape(-1).contiguous().float()
         ops.grid_ema_update(self.occs, cells, occ, ema_decay)
         mean = ops.grid_threshold(self.occs, occ_thre, self._binary_u8())
-        self.occs_mean_host = float(mean.item())
+        self._occs_mean.copy_(mean)                         # stays on the device: no host sync in a grid refresh
+        self._mean_version, self._mean_host = self.occs._version, None
 
     @torch.no_grad()
     def every_n_step(self, step, occ_eval_fn, occ_thre=1e-2, ema_decay=0.95, warmup_steps=256, n=16, **kw):
@@ -119,6 +147,7 @@ class OccupancyGrid(torch.nn.Module):
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._roi_host = self._roi_aabb.detach().cpu().numpy().copy()
+        self._mean_version = None
         return out
 
 

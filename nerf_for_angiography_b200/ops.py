@@ -203,7 +203,7 @@ def grid_query(points, roi_aabb, resolution, binary):
 
 
 # ------------------------------------------------------------------------------------------------ visibility
-def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None, capacity=None, pool=None):
+def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_thre, totals=None, capacity=None, pool=None, thre_cap=None):
     """Visibility mask + compaction.  Returns (ray_idx', t_starts', t_ends', offsets', keep).
 
     alphas / t_starts / t_ends may be capacity-sized (see `march`): only the ranges named by `offsets` are touched.
@@ -211,8 +211,10 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
       capacity=None: the single host sync of this call reads the whole `totals` tensor, so the caller gets totals[0] (e.g.
                      the marcher's count) for free; the python list is returned in place of `keep`.
       capacity=C   : NO host sync -- outputs have C entries (C >= the kept count, e.g. the marcher's capacity), the kept
-                     count stays on the device (offsets'[R] and totals[1])."""
+                     count stays on the device (offsets'[R] and totals[1]).
+    thre_cap (optional float32[1] device tensor): the threshold is min(alpha_thre, thre_cap[0]) -- mean(grid.occs) left on the device."""
     lib = _lib.load()
+    thre_cap = _chk(thre_cap, torch.float32, "thre_cap", 1, allow_none=True)
     alphas = _chk(alphas, torch.float32, "alphas", 1)
     offsets = _chk(offsets, torch.int32, "offsets", 1)
     t_starts = _chk(t_starts, torch.float32, "t_starts", 1)
@@ -221,7 +223,7 @@ def visibility_compact(alphas, offsets, t_starts, t_ends, early_stop_eps, alpha_
     keep = _alloc(pool, "vis_keep", n, torch.uint8, dev)
     kept = torch.empty((R,), dtype=torch.int32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(alphas), _p(offsets), R, float(early_stop_eps), float(alpha_thre), _p(keep), _p(kept),
-                                         None, None, _stream()), "angio_visibility_mask")
+                                         None, None, _p(thre_cap), _stream()), "angio_visibility_mask")
     host_totals = None
     if capacity is not None:
         new_offsets = exclusive_scan(kept, totals[1:2] if totals is not None else None)
@@ -315,7 +317,7 @@ def march_head(rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_pl
 
 
 def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aabb, roi_aabb, resolution, binary, near_plane, far_plane,
-                      step_size, early_stop_eps, alpha_thre, k0=32, totals=None, pool=None, timing=None, head=None):
+                      step_size, early_stop_eps, alpha_thre, k0=32, totals=None, pool=None, timing=None, head=None, thre_cap=None):
     """acc_ray_marching (march -> alpha_fn -> visibility filter -> compaction) with LAZY marching and no host sync:
 
       head   the first k0 samples of every ray, one marching pass (no count / scan: warps reserve their slots atomically),
@@ -332,6 +334,7 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
     lib = _lib.load()
     if precision != PREC_BF16:
         raise ValueError("march_filter_lazy: bf16 path only")
+    thre_cap = _chk(thre_cap, torch.float32, "thre_cap", 1, allow_none=True)
     if not 1 <= k0 <= 32:
         raise ValueError("k0 must be in 1..32")
     rays_o = _chk(rays_o, torch.float32, "ray_origins", 2)
@@ -364,7 +367,7 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
         ev1.record()
         timing.append((ev0, ev1, h_total))
     _lib.check(lib.angio_visibility_head_mask(_p(h_alpha), _p(h_cnt), _p(h_base), R, int(k0), float(early_stop_eps), float(alpha_thre),
-                                              _p(h_keep), _p(h_kept), _p(t_end), _p(alive), _stream()), "angio_visibility_head_mask")
+                                              _p(h_keep), _p(h_kept), _p(t_end), _p(alive), _p(thre_cap), _stream()), "angio_visibility_head_mask")
     # ---- tail of the rays that are still alive (usually few; the kernels do nothing for the others)
     counts = torch.empty((R,), dtype=i32, device=dev)
     runs = _alloc(pool, "lz_runs", int(lib.angio_march_runs_bytes(R)), u8, dev)
@@ -390,7 +393,7 @@ def march_filter_lazy(desc, params, packed, precision, rays_o, rays_d, scene_aab
         timing.append((ev0, ev1, tail_total))
     kept = torch.empty((R,), dtype=i32, device=dev)
     _lib.check(lib.angio_visibility_mask(_p(t_alpha), _p(t_off), R, float(early_stop_eps), float(alpha_thre), _p(t_keep), _p(kept), _p(t_end),
-                                         _p(h_kept), _stream()), "angio_visibility_mask")
+                                         _p(h_kept), _p(thre_cap), _stream()), "angio_visibility_mask")
     # ---- packed result
     new_off = exclusive_scan(kept, totals[1:2] if totals is not None else None)
     ray_idx = _alloc(pool, "kept_idx", cap, i32, dev)
@@ -628,14 +631,14 @@ def signal_peers(peer, tag):
 
 
 def adam_step_allreduce(params, peer, tag, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0,
-                        active_index=-1):
+                        active_index=-1, wait_stats=None):
     """Adam on the rank-ordered sum of all ranks' gradients, read straight from NVLink peer memory (see angio_b200.h)."""
     lib = _lib.load()
     for t, nme in ((params, "params"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
         _chk(t, torch.float32, nme, 1)
     _lib.check(lib.angio_adam_step_allreduce(_p(params), peer.peer_grad_ptrs[tag & 1], peer.world, _p(peer.flags), int(tag) & 0xFFFFFFFF,
                                              _p(exp_avg), _p(exp_avg_sq), params.numel(), float(lr), float(beta1), float(beta2), float(eps),
-                                             int(step), float(grad_scale), int(active_index), _stream()), "angio_adam_step_allreduce")
+                                             int(step), float(grad_scale), int(active_index), _p(wait_stats), _stream()), "angio_adam_step_allreduce")
 
 
 def project_volume(volume, bounds, rays_o, rays_d, depths, kind="ct"):

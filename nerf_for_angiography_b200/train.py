@@ -104,6 +104,9 @@ class Trainer:
         # lazy marching (sync-free loop with early termination): march only the first samples of every ray before the
         # visibility pass and the rest only for rays that are still transparent behind them.  ANGIO_LAZY_MARCH=0: full march.
         self.lazy_march = bool(self.sync_free and self.early_termination and os.environ.get("ANGIO_LAZY_MARCH", "1") != "0")
+        # sampler status of past draws, copied to pinned host memory without waiting and inspected once the copy has landed
+        self._status_host = torch.zeros(2, dtype=torch.int32).pin_memory() if self.dev.type == "cuda" else None
+        self._status_event = None
 
     # ------------------------------------------------------------------ memory plan
     def _plan_memory(self, mode, fraction):
@@ -184,8 +187,9 @@ class Trainer:
         if sync_free and self.lazy_march:                # `marched`, if given, is the head march of these rays (see _march)
             ray_idx, t0, t1, offsets = ops.march_filter_lazy(
                 self.model._desc, self.kflat, self.packed, self.model._precision_id, o, d, self._aabb_host, g._roi_host, g._resolution,
-                g._binary_u8(), self.near, self.far, self.step_size, self.early_stop_eps, min(self.alpha_thre, g.occs_mean_host),
-                k0=min(32, self.early_termination), totals=totals, pool=self.pool_bufs, timing=self.kernel_events, head=marched)
+                g._binary_u8(), self.near, self.far, self.step_size, self.early_stop_eps, self.alpha_thre,
+                k0=min(32, self.early_termination), totals=totals, pool=self.pool_bufs, timing=self.kernel_events, head=marched,
+                thre_cap=g.occs_mean_dev())
             return ray_idx, t0, t1, offsets, None
         ray_idx, t0, t1, offsets = marched if marched is not None else self._march(o, d, totals, pooled=sync_free)
         n_pre = ray_idx.numel()
@@ -205,9 +209,9 @@ class Trainer:
                 if self.kernel_events is not None:
                     ev1.record()
                     self.kernel_events.append((ev0, ev1, totals[0:1] if bf16 else n_pre))
-            thre = min(self.alpha_thre, g.occs_mean_host)
-            ray_idx, t0, t1, offsets, host_totals = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, thre,
-                                                                          totals=totals if bf16 else None,
+            # alpha_thre = min(alpha_thre, mean(occs)) as nerfacc.ray_marching does; the mean is read on the device
+            ray_idx, t0, t1, offsets, host_totals = ops.visibility_compact(alphas, offsets, t0, t1, self.early_stop_eps, self.alpha_thre,
+                                                                          thre_cap=g.occs_mean_dev(), totals=totals if bf16 else None,
                                                                           capacity=cap if sync_free else None,
                                                                           pool=self.pool_bufs if sync_free else None)
             if sync_free:
@@ -228,8 +232,9 @@ class Trainer:
     # ------------------------------------------------------------------ one reference iteration
     def step(self, rays=None):
         """rays: optional (o[R,3], d[R,3], target[R]) -- otherwise sampled from the pool.  Returns a StepResult: `loss` is a
-        device scalar, the sample counts are fetched lazily.  In sync-free mode nothing in here waits for the GPU (except the
-        occupancy-grid refresh every 16th iteration, which reads mean(occs)).
+        device scalar, the sample counts are fetched lazily.  In sync-free mode nothing in here waits for the GPU: mean(occs) of
+        a grid refresh stays on the device (the visibility kernels read it there); only the refreshes after the grid's warm-up
+        (iteration >= 256) pick their cells with torch.nonzero, which synchronises like the reference library does.
 
         Step boundary (sync-free mode, pool sampling): the NEXT iteration's ray batch is drawn and marched between this
         iteration's backward and its optimiser step -- neither depends on the weights -- so the gradient all-reduce runs
@@ -247,28 +252,46 @@ class Trainer:
         else:
             o, d, target = rays
             totals = torch.zeros((4,), dtype=torch.int32, device=self.dev)
+            if self._prefetched is not None and self.lazy_march:
+                # the pending batch's head march lives in the pooled lz_h_* arrays this step is about to reuse: redo it later
+                self._prefetched["marched"] = None
         R = o.shape[0]
         sync_free = self.sync_free and R <= self.n_rays
+        if rays is None and sync_free:
+            self._check_sampler_status(totals)
         self._refresh_packed()
         self.update_grids()
         ray_idx, t0, t1, offsets, n_pre = self.march_and_filter(o, d, totals, sync_free=sync_free, marched=marched)
         n_kept = ray_idx.numel()                                            # sync-free: the capacity, not the count
-        if n_kept > 0:                                                      # run_nerf_acc.py:289
+        have = n_kept > 0                                                   # run_nerf_acc.py:289 (rank-local on the one-sync path)
+        # Data-parallel runs enter the gradient exchange on EVERY iteration: `have` is a rank-local fact on the one-sync path, so
+        # a rank without samples contributes a zero gradient and a zero count instead of skipping the collective its peers
+        # wait in; the all-rank sum of the count slot gates Adam on every rank alike.
+        if have or self.world > 1:
             prec = m._precision_id
-            kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
-            if sync_free:
-                kw["n_dev"] = offsets[R:R + 1]
-            logits, saved = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
-            pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
-                                                             pool=self.pool_bufs if sync_free else None)
             use_peer = self.peer is not None and sync_free
             if use_peer:
                 self.grad, tag = self.peer.next_buffer()                    # this step's gradient lives in NVLink peer memory
-            ops.mlp_backward(m._desc, self.kflat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
-            m._map_grad_(self.grad)                                         # BARF: chain rule through the folded mask (no-op otherwise)
+            if have:
+                kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
+                if sync_free:
+                    kw["n_dev"] = offsets[R:R + 1]
+                logits, saved = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
+                pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
+                                                                 pool=self.pool_bufs if sync_free else None)
+                ops.mlp_backward(m._desc, self.kflat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
+                m._map_grad_(self.grad)                                     # BARF: chain rule through the folded mask (no-op otherwise)
+                loss = loss_sum / R
+            else:
+                self.grad.zero_()
+                loss = torch.full((1,), float("nan"), device=self.dev)
+                pix = torch.ones(R, device=self.dev)
             active = None
             if sync_free:
                 self.grad[-1:].copy_(offsets[R:R + 1])                      # kept count rides behind the gradient
+                active = self.grad[-1:]
+            elif self.world > 1:
+                self.grad[-1:].fill_(float(n_kept))
                 active = self.grad[-1:]
             work = None
             if use_peer:
@@ -280,14 +303,16 @@ class Trainer:
                 self._prefetched = self._draw(march=(self.n_iter + 1) % self.GRID_EVERY != 0)
             if work is not None:
                 work.wait()
+            # n_iter_adam counts optimiser calls; an iteration in which NO rank kept a sample is skipped on the device (`active`)
+            # but still counted here -- it would take 65 536 rays without a single kept sample, and reading the gate back would
+            # cost the host synchronisation this loop exists to avoid.
             if use_peer:                                                    # waits for all tags, sums over NVLink, Adam -- one kernel
                 ops.adam_step_allreduce(self.flat, self.peer, tag, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1,
-                                        active_index=self.flat.numel())
+                                        active_index=self.flat.numel(), wait_stats=self.peer.wait_stats)
             else:
                 ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.n_iter_adam + 1, active=active)
             self.n_iter_adam += 1
             self.lr = self.lr0 * (self.decay_rate ** (self.n_iter / self.decay_steps))   # run_nerf_acc.py:323-328
-            loss = loss_sum / R
         else:
             loss = torch.full((1,), float("nan"), device=self.dev)
             pix = torch.ones(R, device=self.dev)
@@ -298,6 +323,20 @@ class Trainer:
         return self.last
 
     n_iter_adam = 0
+
+    def _check_sampler_status(self, totals):
+        """The on-device ray sampler reports a failed draw (candidate buffer overflow / under-fill; its ids are then all ray 0)
+        in totals[3].  The sync-free loop never reads it, so every 16th step it is copied to pinned host memory without
+        waiting, and a later step raises once that copy has completed."""
+        ev = self._status_event
+        if ev is not None and ev.query():
+            self._status_event = None
+            if int(self._status_host[1]) != 0:
+                raise RuntimeError("ray sampler: candidate buffer overflow / underflow in an earlier draw -- re-draw with a larger threshold")
+        if self._status_event is None and self._status_host is not None and self.n_iter % self.GRID_EVERY == 0:
+            self._status_host.copy_(totals[2:4], non_blocking=True)
+            self._status_event = torch.cuda.Event()
+            self._status_event.record()
 
     # ------------------------------------------------------------------ state capture (benchmark arms start from the same state)
     def snapshot(self):

@@ -59,12 +59,12 @@ def test_argument_validation_without_gpu():
     assert lib.angio_visibility_head(None, None, 10, 0, 0.01, None, None) == _lib.ERR_INVALID_ARG
     assert lib.angio_project_volume(None, 8, 8, 8, None, None, None, 10, None, 4, 1, None, None) == _lib.ERR_INVALID_ARG
     assert lib.angio_signal_peers(None, 2, 0, 1, None) == _lib.ERR_INVALID_ARG
-    assert lib.angio_adam_step_allreduce(None, None, 2, None, 1, None, None, 10, 1e-4, 0.9, 0.999, 1e-8, 1, 1.0, -1, None) == _lib.ERR_INVALID_ARG
+    assert lib.angio_adam_step_allreduce(None, None, 2, None, 1, None, None, 10, 1e-4, 0.9, 0.999, 1e-8, 1, 1.0, -1, None, None) == _lib.ERR_INVALID_ARG
     assert b"angio_adam_step_allreduce" in lib.angio_last_error_string()
     # lazy marching entry points
     assert lib.angio_march_head(None, None, 10, None, None, 32, None, 0.0, 1.0, 0.1, 32, None, None, None, None, None, None, None, None,
                                 None) == _lib.ERR_INVALID_ARG
-    assert lib.angio_visibility_head_mask(None, None, None, 10, 32, 0.01, 0.0, None, None, None, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.angio_visibility_head_mask(None, None, None, 10, 32, 0.01, 0.0, None, None, None, None, None, None) == _lib.ERR_INVALID_ARG
     assert lib.angio_compact_head_tail(None, None, None, None, None, None, None, None, None, None, 10, 0, None, None, None, None) == _lib.ERR_INVALID_ARG
 
 
