@@ -44,6 +44,16 @@ ANGIO_API int angio_sm_count(void);
 /* total number of kernels this library has launched in this process (bench.py's gpu_launches) */
 ANGIO_API int64_t angio_launch_count(void);
 
+/* Per-launch timeline of this library's kernels (measurement only; bench.py's per-kernel rooflines).  Between
+ * angio_profile_start(stream) and angio_profile_stop() every kernel launch of the library first records a CUDA event on
+ * `stream` (which must be the stream the calls are issued on); the time between two consecutive events is the device time
+ * of the earlier launch plus anything the caller enqueued in between.  angio_profile_stop waits for the last event and
+ * returns the number of launches recorded (< 0: error); angio_profile_entry(i, ...) returns launch i's kernel name and
+ * its milliseconds.  One profile at a time, single-threaded use. */
+ANGIO_API int angio_profile_start(void* stream);
+ANGIO_API int64_t angio_profile_stop(void);
+ANGIO_API int angio_profile_entry(int64_t i, char* name_out, int32_t name_cap, float* ms_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Cone-beam ray generation.   Replaces phantomdata/helpers.py:156-175 (get_ray_values) + the
  * .float() cast at nerf/run_nerf_acc.py:88-89 / visualization/visualization.py:330-331.

@@ -31,6 +31,9 @@ PROTOTYPES = {
     "angio_last_error_string": (ctypes.c_char_p, []),
     "angio_sm_count": (c_i32, []),
     "angio_launch_count": (c_i64, []),
+    "angio_profile_start": (c_i32, [c_ptr]),
+    "angio_profile_stop": (c_i64, []),
+    "angio_profile_entry": (c_i32, [c_i64, ctypes.c_char_p, c_i32, ctypes.POINTER(c_f32)]),
     "angio_sample_candidates": (c_i32, [c_ptr, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_sample_rays_workspace_bytes": (c_i64, [c_i32, c_i64]),
     "angio_sample_rays": (c_i32, [c_ptr, c_i64, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),

@@ -11,7 +11,7 @@ namespace angio {
 // thread-local last-error text (angio_last_error_string)
 void set_error(const char* fmt, ...);
 int sm_count();
-void note_launch();  // counts kernel launches (angio_launch_count)
+void note_launch(const char* kernel_name);  // counts kernel launches (angio_launch_count) and feeds the per-launch timeline (angio_profile_*)
 
 inline int finish_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -112,7 +112,7 @@ extern "C" int angio_composite_forward(const float* logits, const float* t_start
                                        int64_t n_rays, const uint8_t* zero_mask, float* pix, void* stream) {
   ANGIO_REQUIRE(offsets && pix && n_rays >= 0, "angio_composite_forward: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); composite_fwd_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(logits, t_starts, t_ends, offsets, n_rays,
+  angio::note_launch("composite_fwd_kernel"); composite_fwd_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(logits, t_starts, t_ends, offsets, n_rays,
                                                                                zero_mask, pix);
   return angio::finish_launch("angio_composite_forward");
 }
@@ -122,7 +122,7 @@ extern "C" int angio_composite_backward(const float* logits, const float* t_star
                                         float* grad_logits, void* stream) {
   ANGIO_REQUIRE(offsets && pix && grad_pix && n_rays >= 0, "angio_composite_backward: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); composite_bwd_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(logits, t_starts, t_ends, offsets, n_rays,
+  angio::note_launch("composite_bwd_kernel"); composite_bwd_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(logits, t_starts, t_ends, offsets, n_rays,
                                                                                zero_mask, pix, grad_pix, grad_logits);
   return angio::finish_launch("angio_composite_backward");
 }
@@ -132,7 +132,7 @@ extern "C" int angio_composite_mse_fused(const float* logits, const float* t_sta
                                          float* grad_logits, float* loss_sum, void* stream) {
   ANGIO_REQUIRE(offsets && target && pix && loss_sum && n_rays >= 0 && n_rays_total > 0, "angio_composite_mse_fused: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); composite_mse_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("composite_mse_kernel"); composite_mse_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
       logits, t_starts, t_ends, offsets, n_rays, target, 1.0f / (float)n_rays_total, pix, grad_logits, loss_sum);
   return angio::finish_launch("angio_composite_mse_fused");
 }

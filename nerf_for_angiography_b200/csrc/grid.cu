@@ -95,7 +95,7 @@ extern "C" int angio_grid_cell_points(const int64_t* cells, const float* jitter,
                                       float* points, void* stream) {
   ANGIO_REQUIRE(jitter && roi_host && points && n >= 0 && res > 0, "angio_grid_cell_points: bad arguments");
   if (n == 0) return 0;
-  angio::note_launch(); cell_points_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(cells, jitter, n, angio::make_roi(roi_host), res, points);
+  angio::note_launch("cell_points_kernel"); cell_points_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(cells, jitter, n, angio::make_roi(roi_host), res, points);
   return angio::finish_launch("angio_grid_cell_points");
 }
 
@@ -107,7 +107,7 @@ extern "C" int angio_grid_ema_update(float* occs, int64_t n_cells, const int64_t
   cudaStream_t st = angio::as_stream(stream);
   if (!cells) {
     ANGIO_REQUIRE(n == n_cells, "angio_grid_ema_update: cells == NULL requires n == n_cells");
-    angio::note_launch(); ema_all_kernel<<<angio::blocks_for(n, 256), 256, 0, st>>>(occs, occ, n, decay);
+    angio::note_launch("ema_all_kernel"); ema_all_kernel<<<angio::blocks_for(n, 256), 256, 0, st>>>(occs, occ, n, decay);
     return angio::finish_launch("angio_grid_ema_update(all)");
   }
   const int64_t need = ((n_cells + 31) / 32) * 4;
@@ -116,8 +116,8 @@ extern "C" int angio_grid_ema_update(float* occs, int64_t n_cells, const int64_t
     return ANGIO_ERR_WORKSPACE;
   }
   ANGIO_CUDA(cudaMemsetAsync(workspace, 0, need, st));
-  angio::note_launch(); ema_decay_kernel<<<angio::blocks_for(n, 256), 256, 0, st>>>(occs, cells, n, decay, reinterpret_cast<uint32_t*>(workspace));
-  angio::note_launch(); ema_max_kernel<<<angio::blocks_for(n, 256), 256, 0, st>>>(occs, cells, occ, n);
+  angio::note_launch("ema_decay_kernel"); ema_decay_kernel<<<angio::blocks_for(n, 256), 256, 0, st>>>(occs, cells, n, decay, reinterpret_cast<uint32_t*>(workspace));
+  angio::note_launch("ema_max_kernel"); ema_max_kernel<<<angio::blocks_for(n, 256), 256, 0, st>>>(occs, cells, occ, n);
   return angio::finish_launch("angio_grid_ema_update");
 }
 
@@ -130,10 +130,10 @@ extern "C" int angio_grid_threshold(const float* occs, int64_t n_cells, float oc
   }
   cudaStream_t st = angio::as_stream(stream);
   float* partials = reinterpret_cast<float*>(workspace);
-  angio::note_launch(); partial_sum_kernel<<<kPartials, 256, 0, st>>>(occs, n_cells, partials);
-  angio::note_launch(); final_mean_kernel<<<1, 256, 0, st>>>(partials, kPartials, n_cells, mean_out);
+  angio::note_launch("partial_sum_kernel"); partial_sum_kernel<<<kPartials, 256, 0, st>>>(occs, n_cells, partials);
+  angio::note_launch("final_mean_kernel"); final_mean_kernel<<<1, 256, 0, st>>>(partials, kPartials, n_cells, mean_out);
   int blocks = angio::blocks_for(n_cells, 256);
   int cap = angio::sm_count() * 8;
-  angio::note_launch(); threshold_kernel<<<blocks > cap ? cap : blocks, 256, 0, st>>>(occs, n_cells, mean_out, occ_thre, binary);
+  angio::note_launch("threshold_kernel"); threshold_kernel<<<blocks > cap ? cap : blocks, 256, 0, st>>>(occs, n_cells, mean_out, occ_thre, binary);
   return angio::finish_launch("angio_grid_threshold");
 }

@@ -436,7 +436,7 @@ extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64
   if (n_rays == 0) return 0;
   Aabb6 aabb;
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
-  angio::note_launch(); march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("march_count_kernel"); march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts,
       run_table_t0(runs, n_rays), run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays), resume_alive);
   return angio::finish_launch("angio_march_count");
@@ -454,7 +454,7 @@ extern "C" int angio_march_head(const float* rays_o, const float* rays_d, int64_
   Aabb6 aabb;
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
   const int rays_per_block = 32 * kWarpsPerBlock;
-  angio::note_launch(); march_head_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("march_head_kernel"); march_head_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, k0, head_idx, head_t0, head_t1,
       head_cnt, head_base, head_total, t_resume, t_max);
   return angio::finish_launch("angio_march_head");
@@ -464,7 +464,7 @@ extern "C" int64_t angio_march_runs_bytes(int64_t n_rays) { return n_rays < 0 ? 
 
 extern "C" int angio_exclusive_scan_i32(const int32_t* counts, int64_t n, int32_t* offsets, int32_t* total_out, void* stream) {
   ANGIO_REQUIRE(offsets && (counts || n == 0) && n >= 0, "angio_exclusive_scan_i32: bad arguments");
-  angio::note_launch(); exclusive_scan_kernel<<<kScanCtas, 1024, 0, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
+  angio::note_launch("exclusive_scan_kernel"); exclusive_scan_kernel<<<kScanCtas, 1024, 0, angio::as_stream(stream)>>>(counts, n, offsets, total_out);
   return angio::finish_launch("angio_exclusive_scan_i32");
 }
 
@@ -477,7 +477,7 @@ extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_write: bad sizes");
   if (n_rays == 0) return 0;
   const int rays_per_block = 32 * kWarpsPerBlock;
-  angio::note_launch(); march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("march_write_kernel"); march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets,
       run_table_t0(const_cast<void*>(runs), n_rays), run_table_t1(const_cast<void*>(runs), n_rays),
       run_table_n(const_cast<void*>(runs), n_rays), run_table_count(const_cast<void*>(runs), n_rays),
@@ -489,6 +489,6 @@ extern "C" int angio_grid_query(const float* points, int64_t n, const float* roi
                                 float* out, void* stream) {
   ANGIO_REQUIRE(points && roi_host && binary && out && n >= 0 && res > 0, "angio_grid_query: bad arguments");
   if (n == 0) return 0;
-  angio::note_launch(); grid_query_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(points, n, make_params(roi_host, res, 1.0f), binary, out);
+  angio::note_launch("grid_query_kernel"); grid_query_kernel<<<angio::blocks_for(n, 256), 256, 0, angio::as_stream(stream)>>>(points, n, make_params(roi_host, res, 1.0f), binary, out);
   return angio::finish_launch("angio_grid_query");
 }

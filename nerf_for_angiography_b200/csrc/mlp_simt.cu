@@ -113,7 +113,7 @@ int launch_sgemm(int M, int N, int64_t K, const float* A, int lda, const float* 
   if (M <= 0 || N <= 0) return 0;
   const int64_t kps = ((K + splits - 1) / splits + BK - 1) / BK * BK;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, splits);
-  angio::note_launch(); sgemm_kernel<A_T, B_T, Epi><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, kps > 0 ? kps : BK, epi);
+  angio::note_launch("sgemm_kernel<A_T, B_T, Epi>"); sgemm_kernel<A_T, B_T, Epi><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, kps > 0 ? kps : BK, epi);
   return angio::finish_launch("sgemm");
 }
 
@@ -235,7 +235,7 @@ int simt_forward(const MlpLayout& L, const float* params, const angio_samples& i
     char* base = reinterpret_cast<char*>(saved);
     float* X0 = reinterpret_cast<float*>(base);
     base += align256(n * L.d_in * 4);
-    angio::note_launch(); encode_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, 0, n, L.basis, coef, X0, L.d_in);
+    angio::note_launch("encode_kernel"); encode_kernel<<<blocks_for(n, 256), 256, 0, st>>>(in, 0, n, L.basis, coef, X0, L.d_in);
     const float* cur = X0; int cur_ld = L.d_in;
     for (int l = 0; l <= L.n_hidden; ++l) {
       float* Y = reinterpret_cast<float*>(base);
@@ -246,7 +246,7 @@ int simt_forward(const MlpLayout& L, const float* params, const angio_samples& i
       cur = Y; cur_ld = L.H;
     }
     const int lo = L.n_linear - 1;
-    angio::note_launch(); out_dot_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>(cur, L.H, n, params + L.off_w[lo], params + L.off_b[lo], in, 0, out_mode, out);
+    angio::note_launch("out_dot_kernel"); out_dot_kernel<<<blocks_for(n * 32, 256), 256, 0, st>>>(cur, L.H, n, params + L.off_w[lo], params + L.off_b[lo], in, 0, out_mode, out);
     return finish_launch("simt_forward(train)");
   }
   const int64_t c = n < kChunk ? n : kChunk;
@@ -261,7 +261,7 @@ int simt_forward(const MlpLayout& L, const float* params, const angio_samples& i
                     reinterpret_cast<float*>(base + align256(c * L.d_in * 4) + align256(c * L.H * 4))};
   for (int64_t i0 = 0; i0 < n; i0 += c) {
     const int64_t m = (n - i0 < c) ? n - i0 : c;
-    angio::note_launch(); encode_kernel<<<blocks_for(m, 256), 256, 0, st>>>(in, i0, m, L.basis, coef, X0, L.d_in);
+    angio::note_launch("encode_kernel"); encode_kernel<<<blocks_for(m, 256), 256, 0, st>>>(in, i0, m, L.basis, coef, X0, L.d_in);
     const float* cur = X0; int cur_ld = L.d_in;
     for (int l = 0; l <= L.n_hidden; ++l) {
       float* Y = bufs[l & 1];
@@ -271,7 +271,7 @@ int simt_forward(const MlpLayout& L, const float* params, const angio_samples& i
       cur = Y; cur_ld = L.H;
     }
     const int lo = L.n_linear - 1;
-    angio::note_launch(); out_dot_kernel<<<blocks_for(m * 32, 256), 256, 0, st>>>(cur, L.H, m, params + L.off_w[lo], params + L.off_b[lo], in, i0, out_mode, out);
+    angio::note_launch("out_dot_kernel"); out_dot_kernel<<<blocks_for(m * 32, 256), 256, 0, st>>>(cur, L.H, m, params + L.off_w[lo], params + L.off_b[lo], in, i0, out_mode, out);
   }
   return finish_launch("simt_forward");
 }
@@ -305,13 +305,13 @@ int simt_backward(const MlpLayout& L, const float* params, const angio_samples& 
   const int lo = L.n_linear - 1;
   const int64_t rows_per_split = (n + kSplits - 1) / kSplits;
   // output layer: d b_out = sum g ; d w_out[o] = sum_s g[s] * a_last[s][o]
-  angio::note_launch(); vecsum_partial_kernel<<<kSplits, 256, 0, st>>>(grad_out, n, rows_per_split, partial);
-  angio::note_launch(); sum_partials_kernel<<<1, 256, 0, st>>>(partial, kSplits, 1, grad_params + L.off_b[lo]);
-  angio::note_launch(); colsum_partial_kernel<<<dim3((H + 255) / 256, kSplits), 256, 0, st>>>(act[L.n_hidden], grad_out, H, n, rows_per_split, partial);
-  angio::note_launch(); sum_partials_kernel<<<blocks_for(H, 256), 256, 0, st>>>(partial, kSplits, H, grad_params + L.off_w[lo]);
+  angio::note_launch("vecsum_partial_kernel"); vecsum_partial_kernel<<<kSplits, 256, 0, st>>>(grad_out, n, rows_per_split, partial);
+  angio::note_launch("sum_partials_kernel"); sum_partials_kernel<<<1, 256, 0, st>>>(partial, kSplits, 1, grad_params + L.off_b[lo]);
+  angio::note_launch("colsum_partial_kernel"); colsum_partial_kernel<<<dim3((H + 255) / 256, kSplits), 256, 0, st>>>(act[L.n_hidden], grad_out, H, n, rows_per_split, partial);
+  angio::note_launch("sum_partials_kernel"); sum_partials_kernel<<<blocks_for(H, 256), 256, 0, st>>>(partial, kSplits, H, grad_params + L.off_w[lo]);
   // delta of the last hidden layer
   float* dz = dbuf[0];
-  angio::note_launch(); dout_kernel<<<blocks_for(n * H, 256), 256, 0, st>>>(grad_out, params + L.off_w[lo], act[L.n_hidden], H, n, dz);
+  angio::note_launch("dout_kernel"); dout_kernel<<<blocks_for(n * H, 256), 256, 0, st>>>(grad_out, params + L.off_w[lo], act[L.n_hidden], H, n, dz);
   for (int l = L.n_hidden; l >= 0; --l) {
     const float* a_in = (l == 0) ? X0 : act[l - 1];
     const int K_in = L.in_dim[l];
@@ -320,10 +320,10 @@ int simt_backward(const MlpLayout& L, const float* params, const angio_samples& 
       EpiPartial epi{partial, H, K_in};
       int rc = launch_sgemm<true, false>(H, K_in, n, dz, H, a_in, K_in, kSplits, epi, st);
       if (rc) return rc;
-      angio::note_launch(); sum_partials_kernel<<<blocks_for((int64_t)H * K_in, 256), 256, 0, st>>>(partial, kSplits, (int64_t)H * K_in, grad_params + L.off_w[l]);
+      angio::note_launch("sum_partials_kernel"); sum_partials_kernel<<<blocks_for((int64_t)H * K_in, 256), 256, 0, st>>>(partial, kSplits, (int64_t)H * K_in, grad_params + L.off_w[l]);
     }
-    angio::note_launch(); colsum_partial_kernel<<<dim3((H + 255) / 256, kSplits), 256, 0, st>>>(dz, nullptr, H, n, rows_per_split, partial);
-    angio::note_launch(); sum_partials_kernel<<<blocks_for(H, 256), 256, 0, st>>>(partial, kSplits, H, grad_params + L.off_b[l]);
+    angio::note_launch("colsum_partial_kernel"); colsum_partial_kernel<<<dim3((H + 255) / 256, kSplits), 256, 0, st>>>(dz, nullptr, H, n, rows_per_split, partial);
+    angio::note_launch("sum_partials_kernel"); sum_partials_kernel<<<blocks_for(H, 256), 256, 0, st>>>(partial, kSplits, H, grad_params + L.off_b[l]);
     // data gradient
     if (l > 0) {
       float* dnext = dbuf[(dz == dbuf[0]) ? 1 : 0];
@@ -336,8 +336,8 @@ int simt_backward(const MlpLayout& L, const float* params, const angio_samples& 
       int rc = launch_sgemm<false, false>((int)n, L.d_in, H, dz, H, params + L.off_w[0], L.d_in, 1, epi, st);
       if (rc) return rc;
       const int nb = 3 * L.basis;
-      angio::note_launch(); coef_grad_partial_kernel<<<dim3(nb, kSplits), 256, 0, st>>>(X0, dX0, L.d_in, L.basis, n, rows_per_split, partial);
-      angio::note_launch(); sum_partials_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(partial, kSplits, nb, grad_params + L.off_coef);
+      angio::note_launch("coef_grad_partial_kernel"); coef_grad_partial_kernel<<<dim3(nb, kSplits), 256, 0, st>>>(X0, dX0, L.d_in, L.basis, n, rows_per_split, partial);
+      angio::note_launch("sum_partials_kernel"); sum_partials_kernel<<<blocks_for(nb, 256), 256, 0, st>>>(partial, kSplits, nb, grad_params + L.off_coef);
     }
   }
   return finish_launch("simt_backward");

@@ -35,6 +35,8 @@
 // First-layer K layout: [x_hi(3) x_lo(3) (sin_j, cos_j) x 3L, 0-pad] -- world coordinates reach +-173 and bf16 keeps 8
 // bits, so x enters as a hi/lo bf16 pair against duplicated weight columns.  The phase a = fl(fl(2 pi x) c) is computed
 // exactly as the reference does in fp32, reduced by 2 pi with a two-constant Cody-Waite step, then sin/cos use the SFU.
+#include <stdlib.h>
+
 #include "mlp_layout.cuh"
 #include "tc05.cuh"
 
@@ -512,6 +514,229 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------ (1b) forward, three tile slots
+// Inference forward (visibility pass, occupancy refresh, rendering) with THREE 128-sample tiles in flight per CTA.
+//
+// Why three.  A slot's per-layer chain is  MMA issue 512 cycles + pipe drain ~330 + barrier observation ~165 + epilogue ~560 +
+// hand-off ~190 ~= 1750 cycles, of which the tensor pipe works 512: two slots can keep it at most ~58 % busy (measured: 35 %),
+// three could reach ~87 %.  TMEM has 512 columns; the two-slot kernel spends 128 accumulator + 64 operand (+ 32 feature) columns
+// per slot, so a third slot does not fit that way.
+//
+// How it fits.  The epilogue warp that drained 64 accumulator columns of its 32 lanes owns exactly those cells, so it writes the
+// 32 packed bf16x2 words of the next layer's A operand straight back into the first half of them (no other warp ever touches
+// them).  A slot then needs ONE 128-column region while it is in its epilogue and a second one only while its MMA runs (the
+// accumulator being written).  The tensor pipe executes MMAs one after the other, so a single spare region is enough:
+// 3 slots + 1 spare = 4 x 128 columns = all of TMEM.  All MMAs are issued by ONE thread in strict rotation
+// (slot 0, 1, 2, 0, ...): MMA number m reads its A operand from region m % 4 and writes its accumulator to region (m + 3) % 4,
+// which is the region MMA m - 1 (previous slot, already issued, executes earlier in the in-order tensor pipe) read its A from.
+// The slot's next stage is MMA m + 3 and reads region (m + 3) % 4: the epilogue's in-place operand.
+//   region layout (128 fp32 columns, lane = sample row):  hidden-layer A operand: K-steps 0..3 (hidden 0..63) in columns [0, 32),
+//   K-steps 4..7 (hidden 64..127) in columns [64, 96) -- each column half is written by the warp that owns it;
+//   first-layer features: 16-column chunk c (K-step c) in columns (c & 1) * 64 + (c >> 1) * 8.
+// Threads: warp 0 = weight load + the MMA issuer, warps 1..24 = three tile groups of 8 warps (4 TMEM lane quadrants x 2 column
+// halves).  25 warps leave 80 registers per thread, so an epilogue handles its 64 columns in two passes of 32.
+constexpr int kSlots3 = 3;
+constexpr int kThreads3 = 32 + kSlots3 * kGroupThreads;   // 800
+
+struct __align__(8) PipeBarriers3 {
+  uint64_t w_ready;
+  uint64_t a_ready[kSlots3];
+  uint64_t acc_ready[kSlots3];
+  uint32_t tmem_base;
+};
+
+// 32 accumulator columns (+ bias) -> this pass's share of the output dot product (LAST) or 16 packed bf16x2 words (relu'd)
+template <bool LAST>
+__device__ __forceinline__ float bias_relu_32(const uint32_t (&r)[32], const float* __restrict__ bias, const float* __restrict__ w_out,
+                                              uint32_t (&pk)[16]) {
+  float dot0 = 0.0f, dot1 = 0.0f;
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * jj);
+    const float2 u0 = __fadd2_rn(make_float2(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1])), make_float2(b0.x, b0.y));
+    const float2 u1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3])), make_float2(b0.z, b0.w));
+    if (LAST) {
+      const float4 w0 = *reinterpret_cast<const float4*>(w_out + 4 * jj);
+      dot0 = fmaf(fmaxf(u0.x, 0.f), w0.x, dot0); dot1 = fmaf(fmaxf(u0.y, 0.f), w0.y, dot1);
+      dot0 = fmaf(fmaxf(u1.x, 0.f), w0.z, dot0); dot1 = fmaf(fmaxf(u1.y, 0.f), w0.w, dot1);
+    } else {
+      pk[2 * jj] = pack_bf16x2_relu(u0.x, u0.y);
+      pk[2 * jj + 1] = pack_bf16x2_relu(u1.x, u1.y);
+    }
+  }
+  return dot0 + dot1;
+}
+
+template <int OUT_MODE>
+__global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
+                                                                   float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ PipeBarriers3 bars;
+  __shared__ float s_dot[kSlots3][kTile];                                  // output layer: column-half 1's partial dot products
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
+  const int lane = threadIdx.x % 32;
+  int64_t n = in.n;
+  if (in.n_dev) { const int64_t nd = *in.n_dev; n = nd < n ? nd : n; }     // device-resident count (sync-free marcher -> MLP)
+  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...; slot = j % 3.  Every slot runs the same number of rounds (the
+  // strict MMA rotation needs that); tiles past the end are computed on zero inputs and not stored.
+  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t rounds = (my_tiles + kSlots3 - 1) / kSlots3;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars.w_ready, 1);
+    for (int s = 0; s < kSlots3; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); }
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(&bars.tmem_base, kTmemCols); tmem_relinquish(); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (bars.tmem_base != 0) __trap();                   // one CTA per SM owning all 512 columns: the regions are compile-time columns
+  const float* consts = reinterpret_cast<const float*>(smem + P.off_const);
+  const int n_stages = P.n_hidden + 1;                 // L+1 layers with N = 128; the 128 -> 1 output layer is a dot product in the last epilogue
+
+  if (warp == 0) {
+    // ===================== weight load + the one MMA issuer =====================
+    if (lane == 0) load_weight_image(smem, packed, P.total_bytes, &bars.w_ready);
+    mbar_wait(&bars.w_ready, 0);
+    const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 0);
+    const uint32_t smem_base = smem_u32(smem);
+    const int k0_steps = P.k0_pad / 16;
+    uint32_t m = 0;                                    // MMA sequence number: A from region m % 4, D into region (m + 3) % 4
+    uint32_t phase = 0;                                // all slots flip together: one full rotation per (round, stage)
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+      for (int st = 0; st < n_stages; ++st) {
+        const uint32_t wbase = smem_base + w_offset(st);
+#pragma unroll
+        for (int s = 0; s < kSlots3; ++s, ++m) {
+          mbar_wait(&bars.a_ready[s], phase);
+          fence_after_sync();
+          if (lane == 0) {
+            const uint32_t a_reg = (m & 3u) * 128u, d_reg = ((m + 3u) & 3u) * 128u;
+            if (st == 0) {
+              for (int k = 0; k < k0_steps; ++k)
+                mma_ts(d_reg, a_reg + (k & 1) * 64 + (k >> 1) * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, k > 0);
+            } else {
+#pragma unroll
+              for (int k = 0; k < kH / 16; ++k)
+                mma_ts(d_reg, a_reg + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc,
+                       k > 0);
+            }
+            mma_commit(&bars.acc_ready[s]);
+          }
+          __syncwarp();
+        }
+        phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== tile groups: features, epilogues, output =====================
+    const int g = (warp - 1) / 8;                 // slot
+    const int q = warp % 4;                       // TMEM lane quadrant (hardware rule: warp w accesses lanes 32 * (w % 4) ..)
+    const int h = ((warp - 1) % 8) / 4;           // column half
+    const int row = q * 32 + lane;                // sample row inside the tile
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    mbar_wait(&bars.w_ready, 0);                  // biases / coefficients live in the packed image
+    const float* coef = consts + (P.n_hidden + 2) * 128 + 4;
+    const float b_out = consts[(P.n_hidden + 2) * 128];
+    const float* w_out = consts + (P.n_hidden + 1) * 128 + h * 64;   // fp32 output weights of this warp's columns
+    const int pair_bar = 1 + g * 4 + q;           // named barrier shared by the two column-half warps of this row quadrant
+    const int nb = 3 * P.basis;
+    uint32_t phase = 0;
+    auto fetch = [&](int64_t jt, float (&xx)[3], float& dtt, bool& vv, int64_t& idx) {
+      int64_t ii = (blockIdx.x + jt * gridDim.x) * kTile + row;
+      vv = (jt < my_tiles) && (ii < n);
+      xx[0] = xx[1] = xx[2] = 0.f;
+      dtt = 0.f;
+      if (vv) {
+        if (in.sample_idx) ii = in.sample_idx[ii];      // index list: a subset of the sample arrays (two-phase visibility pass)
+        angio::sample_position(in, ii, xx);
+        if (OUT_MODE == ANGIO_OUT_ALPHA) dtt = in.t_ends[ii] - in.t_starts[ii];
+      }
+      idx = ii;
+    };
+    // this warp's share of the first-layer features: half 0 encodes chunks 0 and 2, half 1 chunk 1 (and 3 when K0 > 48)
+    auto encode = [&](const float (&xx)[3], uint32_t (&f0)[8], uint32_t (&f1)[8]) {
+      encode_feature_chunk(xx, coef, nb, h, f0);
+      if ((2 + h) * 16 < P.k0_pad) encode_feature_chunk(xx, coef, nb, 2 + h, f1);
+    };
+    auto store_features = [&](uint32_t region, const uint32_t (&f0)[8], const uint32_t (&f1)[8]) {
+      const uint32_t base = region + lane_off + h * 64;
+      tmem_st8(base, f0);
+      if ((2 + h) * 16 < P.k0_pad) tmem_st8(base + 8, f1);
+    };
+    float xn[3], dtn;
+    bool vn;
+    int64_t in_;
+    uint32_t f0[8], f1[8];
+    fetch(g, xn, dtn, vn, in_);
+    encode(xn, f0, f1);
+    store_features((uint32_t)g * 128u, f0, f1);           // MMA number g reads region g
+    signal_a_ready(&bars.a_ready[g], lane);
+    for (int64_t rd = 0; rd < rounds; ++rd) {
+      const int64_t j = rd * kSlots3 + g;
+      const int64_t i = in_;                      // where this row's output goes
+      const bool valid = vn;
+      const float dt = dtn;
+      const bool more = rd + 1 < rounds;
+      if (more) fetch(j + kSlots3, xn, dtn, vn, in_);   // in flight during this tile's layers
+      uint32_t m = (uint32_t)(rd * n_stages) * kSlots3 + g;    // MMA number of this tile's stage 0 (mod 2^32 keeps m % 4)
+      // ---- hidden layers: acc + bias -> relu -> bf16 -> in-place A operand of the next layer (this warp: columns [64h, 64h+64))
+      for (int l = 0; l < P.n_hidden; ++l, m += kSlots3) {
+        const uint32_t reg = ((m + 3u) & 3u) * 128u + lane_off + h * 64;
+        mbar_wait(&bars.acc_ready[g], phase);
+        phase ^= 1;
+        fence_after_sync();
+        const float* bias = consts + l * 128 + h * 64;
+        uint32_t r[32], pk[16];
+        tmem_ld32(reg, r);
+        wait_ld();
+        bias_relu_32<false>(r, bias, nullptr, pk);
+        tmem_ld32(reg + 32, r);                    // second pass; the first 16 words go back underneath it
+        tmem_st16(reg, pk);
+        wait_ld();
+        bias_relu_32<false>(r, bias + 32, nullptr, pk);
+        tmem_st16(reg + 16, pk);
+        signal_a_ready(&bars.a_ready[g], lane);
+      }
+      // ---- last hidden layer + output layer: logit = w_out . relu(z_{L+1}) + b_out on the CUDA cores, in fp32
+      {
+        const int l = P.n_hidden;
+        const uint32_t reg = ((m + 3u) & 3u) * 128u + lane_off + h * 64;
+        if (more) encode(xn, f0, f1);              // next tile's features, computed while the tensor core runs this tile's last layer
+        mbar_wait(&bars.acc_ready[g], phase);
+        phase ^= 1;
+        fence_after_sync();
+        const float* bias = consts + l * 128 + h * 64;
+        uint32_t r[32], pk[16];
+        tmem_ld32(reg, r);
+        wait_ld();
+        float dot = bias_relu_32<true>(r, bias, w_out, pk);
+        tmem_ld32(reg + 32, r);
+        wait_ld();
+        // the accumulator is in registers: hand the slot's next tile to the tensor core BEFORE finishing this tile's math.  The
+        // features go into the region just drained: it is the A region of this slot's next MMA (number m + 3).
+        if (more) {
+          store_features(((m + 3u) & 3u) * 128u, f0, f1);
+          signal_a_ready(&bars.a_ready[g], lane);
+        }
+        dot += bias_relu_32<true>(r, bias + 32, w_out + 32, pk);
+        // the h = 1 warp hands its half of the dot product to the h = 0 warp of the same row quadrant
+        if (h == 1) {
+          s_dot[g][row] = dot;
+          asm volatile("bar.arrive %0, 64;" ::"r"(pair_bar) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+          if (valid && j < my_tiles) out[i] = out_transform<OUT_MODE>(dot + s_dot[g][row] + b_out, dt);
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(0, kTmemCols);
+}
+
 // ------------------------------------------------------------------------------------------------ (2) data-gradient chain
 // delta images out: [delta_1: n_tiles x 32 KB] ... [delta_{L+1}]; coef_partials: [gridDim.x][32] floats
 __global__ void __launch_bounds__(kThreads, 1) mlp_dgrad_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
@@ -929,7 +1154,7 @@ int tc_pack_weights(const MlpLayout& L, const float* params, void* packed, cudaS
   if (!make_plan(L, &P)) { set_error("tc_pack_weights: unsupported shape"); return ANGIO_ERR_UNSUPPORTED; }
   const int n_w_elems = (16384 + P.n_hidden * 32768 + 4096) / 2;
   const int total = n_w_elems > P.n_const ? n_w_elems : P.n_const;
-  angio::note_launch(); pack_kernel<<<blocks_for(total, 256), 256, 0, st>>>(params, L, P, reinterpret_cast<uint8_t*>(packed));
+  angio::note_launch("pack_kernel"); pack_kernel<<<blocks_for(total, 256), 256, 0, st>>>(params, L, P, reinterpret_cast<uint8_t*>(packed));
   return finish_launch("tc_pack_weights");
 }
 
@@ -946,15 +1171,37 @@ static int ensure_smem(K kernel, size_t smem, size_t* cached) {
   return 0;
 }
 
+template <int MODE>
+static int launch_fwd3(const TcPlan& P, const void* packed, const angio_samples& in, float* out, cudaStream_t st) {
+  const size_t smem = (size_t)P.total_bytes + 1024;
+  static size_t cached = 0;
+  if (int rc = ensure_smem(mlp_fwd3_tc_kernel<MODE>, smem, &cached)) return rc;
+  const int64_t n_tiles = (in.n + kTile - 1) / kTile;
+  int grid = sm_count();
+  if (n_tiles < grid) grid = (int)n_tiles;
+  angio::note_launch(MODE == ANGIO_OUT_ALPHA ? "mlp_fwd_tc_kernel<ALPHA>" : MODE == ANGIO_OUT_SIGMA ? "mlp_fwd_tc_kernel<SIGMA>" : "mlp_fwd_tc_kernel<LOGIT>");
+  mlp_fwd3_tc_kernel<MODE><<<grid, kThreads3, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
+  return finish_launch("mlp_fwd3_tc_kernel");
+}
+
+// ANGIO_FWD_SLOTS=2 keeps the two-slot inference forward (A/B measurements); default: three slots
+static bool use_three_slots() {
+  const char* e = getenv("ANGIO_FWD_SLOTS");       // read per call: tools/time_fwd.py switches it inside one process
+  return !(e && e[0] == '2');
+}
+
 template <int MODE, bool TRAIN>
 static int launch_fwd(const TcPlan& P, const void* packed, const angio_samples& in, float* out, void* saved, cudaStream_t st) {
+  if (!TRAIN && use_three_slots()) return launch_fwd3<MODE>(P, packed, in, out, st);
   const size_t smem = (TRAIN && P.stage_off > 0) ? (size_t)P.stage_off + kStageBytesTotal + 1024 : (size_t)P.total_bytes + 1024;
   static size_t cached = 0;
   if (int rc = ensure_smem(mlp_fwd_tc_kernel<MODE, TRAIN>, smem, &cached)) return rc;
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
   int grid = sm_count();
   if (n_tiles < grid) grid = (int)n_tiles;
-  angio::note_launch(); mlp_fwd_tc_kernel<MODE, TRAIN><<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out,
+  angio::note_launch(TRAIN ? "mlp_fwd_tc_kernel<LOGIT,train>" : MODE == ANGIO_OUT_ALPHA ? "mlp_fwd_tc_kernel<ALPHA>"
+                     : MODE == ANGIO_OUT_SIGMA ? "mlp_fwd_tc_kernel<SIGMA>" : "mlp_fwd_tc_kernel<LOGIT>");
+  mlp_fwd_tc_kernel<MODE, TRAIN><<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out,
                                                                                     reinterpret_cast<uint8_t*>(saved));
   return finish_launch("mlp_fwd_tc_kernel");
 }
@@ -1013,10 +1260,10 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
     if (int rc = ensure_smem(mlp_dgrad_tc_kernel, smem, &cached)) return rc;
     int grid = sm_count();
     if (n_tiles < grid) grid = (int)n_tiles;
-    angio::note_launch(); mlp_dgrad_tc_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, sv, grad_out, delta, cpart);
+    angio::note_launch("mlp_dgrad_tc_kernel"); mlp_dgrad_tc_kernel<<<grid, kThreads, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, sv, grad_out, delta, cpart);
     if (int rc = finish_launch("mlp_dgrad_tc_kernel")) return rc;
     if (L.enc) {
-      angio::note_launch(); small_reduce_kernel<<<3 * L.basis, 128, 0, st>>>(cpart, grid, 32, 3 * L.basis, grad_params + L.off_coef, 3 * L.basis, nullptr);
+      angio::note_launch("small_reduce_kernel"); small_reduce_kernel<<<3 * L.basis, 128, 0, st>>>(cpart, grid, 32, 3 * L.basis, grad_params + L.off_coef, 3 * L.basis, nullptr);
     }
   }
   // (3) weight gradients
@@ -1024,16 +1271,16 @@ int tc_backward(const MlpLayout& L, const float* params, const void* packed, con
     const size_t smem = 4096 + (size_t)kWgStages * 65536 + 1024;
     static size_t cached = 0;
     if (int rc = ensure_smem(mlp_wgrad_tc_kernel, smem, &cached)) return rc;
-    angio::note_launch(); mlp_wgrad_tc_kernel<<<nl * G, kWgThreads, smem, st>>>(sv, delta, n_tiles, in.n_dev, L.n_hidden, G, wpart);
+    angio::note_launch("mlp_wgrad_tc_kernel"); mlp_wgrad_tc_kernel<<<nl * G, kWgThreads, smem, st>>>(sv, delta, n_tiles, in.n_dev, L.n_hidden, G, wpart);
     if (int rc = finish_launch("mlp_wgrad_tc_kernel")) return rc;
-    angio::note_launch(); wgrad_reduce_kernel<<<dim3((kWgPartial + 255) / 256, nl), 256, 0, st>>>(wpart, G, L, P, grad_params);
+    angio::note_launch("wgrad_reduce_kernel"); wgrad_reduce_kernel<<<dim3((kWgPartial + 255) / 256, nl), 256, 0, st>>>(wpart, G, L, P, grad_params);
   }
   // output layer
   {
     const uint8_t* a_last = sv + n_tiles * kA0Bytes + (int64_t)L.n_hidden * n_tiles * kActBytes;
-    angio::note_launch(); outgrad_partial_kernel<<<kOutgradBlocks, 256, 0, st>>>(a_last, grad_out, n, in.n_dev, opart);
+    angio::note_launch("outgrad_partial_kernel"); outgrad_partial_kernel<<<kOutgradBlocks, 256, 0, st>>>(a_last, grad_out, n, in.n_dev, opart);
     const int lo = L.n_linear - 1;
-    angio::note_launch(); small_reduce_kernel<<<129, 128, 0, st>>>(opart, kOutgradBlocks, 132, 129, grad_params + L.off_w[lo], 128, grad_params + L.off_b[lo]);
+    angio::note_launch("small_reduce_kernel"); small_reduce_kernel<<<129, 128, 0, st>>>(opart, kOutgradBlocks, 132, 129, grad_params + L.off_w[lo], 128, grad_params + L.off_b[lo]);
   }
   return finish_launch("tc_backward");
 }

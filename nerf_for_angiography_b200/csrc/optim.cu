@@ -101,7 +101,7 @@ extern "C" int angio_signal_peers(void* const* peer_flags_host, int32_t world, i
   ANGIO_REQUIRE(peer_flags_host && world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "angio_signal_peers: bad arguments");
   PeerFlags f;
   for (int r = 0; r < world; ++r) f.flags[r] = reinterpret_cast<uint32_t*>(peer_flags_host[r]);
-  angio::note_launch(); signal_peers_kernel<<<1, 32, 0, angio::as_stream(stream)>>>(f, world, rank, tag);
+  angio::note_launch("signal_peers_kernel"); signal_peers_kernel<<<1, 32, 0, angio::as_stream(stream)>>>(f, world, rank, tag);
   return angio::finish_launch("angio_signal_peers");
 }
 
@@ -123,7 +123,7 @@ extern "C" int angio_adam_step_allreduce(float* params, const void* const* peer_
   }();
   int blocks = angio::blocks_for(n, 256);
   const int cap = angio::sm_count() * 8;
-  angio::note_launch(); adam_allreduce_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("adam_allreduce_kernel"); adam_allreduce_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(
       params, pp, world, my_flags, tag, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, (float)((double)lr / bc1), (float)sqrt(bc2), grad_scale,
       active_index, timeout_ns, wait_stats);
   return angio::finish_launch("angio_adam_step_allreduce");
@@ -137,7 +137,7 @@ extern "C" int angio_adam_step(float* params, const float* grads, float* exp_avg
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   int blocks = angio::blocks_for(n, 256);
   int cap = angio::sm_count() * 8;
-  angio::note_launch(); adam_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+  angio::note_launch("adam_kernel"); adam_kernel<<<blocks > cap ? cap : blocks, 256, 0, angio::as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                                 beta2, eps, (float)((double)lr / bc1), (float)sqrt(bc2), grad_scale, active);
   return angio::finish_launch("angio_adam_step");
 }

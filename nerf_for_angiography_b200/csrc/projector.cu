@@ -71,7 +71,7 @@ extern "C" int angio_project_volume(const float* volume, int32_t nx, int32_t ny,
     v.lo[k] = bounds_host[k];
     v.scale[k] = (float)(n[k] - 1) / (bounds_host[3 + k] - bounds_host[k]);
   }
-  angio::note_launch(); project_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(volume, v, rays_o, rays_d, n_rays, depths,
+  angio::note_launch("project_kernel"); project_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(volume, v, rays_o, rays_d, n_rays, depths,
                                                                                                        n_depths, ct_mode, out);
   return angio::finish_launch("angio_project_volume");
 }

@@ -56,7 +56,7 @@ extern "C" int angio_raygen(const double* cam2world, int32_t view0, const int32_
   int blocks = angio::blocks_for(n, 256);
   int cap = angio::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  angio::note_launch(); raygen_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(cam2world, view0, view_ids, px, py, n, img_w, img_h, focal,
+  angio::note_launch("raygen_kernel"); raygen_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(cam2world, view0, view_ids, px, py, n, img_w, img_h, focal,
                                                              pixels, rays_o, rays_d, pix_out);
   return angio::finish_launch("angio_raygen");
 }

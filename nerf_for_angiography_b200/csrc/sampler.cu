@@ -318,7 +318,7 @@ extern "C" int angio_sample_candidates(const float* weights, int64_t n_pool, uin
   int blocks = angio::blocks_for(n_pool, 256);
   const int cap = angio::sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  angio::note_launch(); sample_candidates_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(weights, n_pool, seed, tau, capacity, cand_keys, cand_ids, counter);
+  angio::note_launch("sample_candidates_kernel"); sample_candidates_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(weights, n_pool, seed, tau, capacity, cand_keys, cand_ids, counter);
   return angio::finish_launch("angio_sample_candidates");
 }
 
@@ -357,14 +357,14 @@ extern "C" int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n
   while (n_buckets < kMaxBuckets && (int64_t)n_buckets * 32 < n) { n_buckets <<= 1; ++log2b; }
   int sweep_blocks = angio::blocks_for(capacity, 1024);
   if (sweep_blocks > angio::sm_count()) sweep_blocks = angio::sm_count();
-  angio::note_launch(); radix_hist_kernel<0><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch(); radix_hist_kernel<1><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch(); radix_hist_kernel<2><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch(); select_finish_kernel<<<1, kSelThreads, 0, st>>>(ctl, capacity, (int32_t)n, hists, status, ids_out);
-  angio::note_launch(); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, seed, log2b, bcount);
-  angio::note_launch(); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, n_buckets, log2b, bcount, bfill,
+  angio::note_launch("radix_hist_kernel<0>"); radix_hist_kernel<0><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
+  angio::note_launch("radix_hist_kernel<1>"); radix_hist_kernel<1><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
+  angio::note_launch("radix_hist_kernel<2>"); radix_hist_kernel<2><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
+  angio::note_launch("select_finish_kernel"); select_finish_kernel<<<1, kSelThreads, 0, st>>>(ctl, capacity, (int32_t)n, hists, status, ids_out);
+  angio::note_launch("mark_kernel"); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, seed, log2b, bcount);
+  angio::note_launch("scatter_kernel"); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, n_buckets, log2b, bcount, bfill,
                                                                           bstart, tmp_hash, tmp_ids);
-  angio::note_launch(); bucket_sort_kernel<<<angio::blocks_for(n_buckets, 8), 256, 0, st>>>(ctl, capacity, (int32_t)n, n_buckets, bstart, tmp_hash,
+  angio::note_launch("bucket_sort_kernel"); bucket_sort_kernel<<<angio::blocks_for(n_buckets, 8), 256, 0, st>>>(ctl, capacity, (int32_t)n, n_buckets, bstart, tmp_hash,
                                                                                         tmp_ids, ids_out);
   return angio::finish_launch("angio_sample_rays");
 }
@@ -378,6 +378,6 @@ extern "C" int angio_raygen_flat(const double* cam2world, const int64_t* ids, in
   int blocks = angio::blocks_for(n, 256);
   const int cap = angio::sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  angio::note_launch(); raygen_flat_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(cam2world, ids, n, img_w, img_h, focal, pixels, rays_o, rays_d, pix_out);
+  angio::note_launch("raygen_flat_kernel"); raygen_flat_kernel<<<blocks, 256, 0, angio::as_stream(stream)>>>(cam2world, ids, n, img_w, img_h, focal, pixels, rays_o, rays_d, pix_out);
   return angio::finish_launch("angio_raygen_flat");
 }

@@ -220,7 +220,7 @@ extern "C" int angio_visibility_mask(const float* alphas, const int32_t* offsets
                                      const int32_t* base_counts, const float* alpha_thre_cap, void* stream) {
   ANGIO_REQUIRE(offsets && kept_counts && n_rays >= 0, "angio_visibility_mask: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
+  angio::note_launch("visibility_mask_kernel"); visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
                                                                                  alpha_thre, keep, kept_counts, t_init, base_counts, alpha_thre_cap);
   return angio::finish_launch("angio_visibility_mask");
 }
@@ -229,7 +229,7 @@ extern "C" int angio_ray_segment_counts(const int32_t* offsets, int64_t n_rays, 
                                        int32_t* counts, void* stream) {
   ANGIO_REQUIRE(offsets && counts && n_rays >= 0 && skip >= 0, "angio_ray_segment_counts: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); segment_counts_kernel<<<angio::blocks_for(n_rays, 256), 256, 0, angio::as_stream(stream)>>>(offsets, n_rays, skip, limit, alive, counts);
+  angio::note_launch("segment_counts_kernel"); segment_counts_kernel<<<angio::blocks_for(n_rays, 256), 256, 0, angio::as_stream(stream)>>>(offsets, n_rays, skip, limit, alive, counts);
   return angio::finish_launch("angio_ray_segment_counts");
 }
 
@@ -237,7 +237,7 @@ extern "C" int angio_ray_segment_ids(const int32_t* offsets, const int32_t* seg_
                                      void* stream) {
   ANGIO_REQUIRE(offsets && seg_offsets && sample_ids && n_rays >= 0 && skip >= 0, "angio_ray_segment_ids: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); segment_ids_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(offsets, seg_offsets, n_rays, skip, sample_ids);
+  angio::note_launch("segment_ids_kernel"); segment_ids_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(offsets, seg_offsets, n_rays, skip, sample_ids);
   return angio::finish_launch("angio_ray_segment_ids");
 }
 
@@ -245,7 +245,7 @@ extern "C" int angio_visibility_head(const float* alphas, const int32_t* offsets
                                      uint8_t* alive, void* stream) {
   ANGIO_REQUIRE(alphas && offsets && alive && n_rays >= 0 && k0 > 0, "angio_visibility_head: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); visibility_head_kernel<<<angio::blocks_for(n_rays, 256), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, k0, early_stop_eps, alive);
+  angio::note_launch("visibility_head_kernel"); visibility_head_kernel<<<angio::blocks_for(n_rays, 256), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, k0, early_stop_eps, alive);
   return angio::finish_launch("angio_visibility_head");
 }
 
@@ -255,7 +255,7 @@ extern "C" int angio_visibility_head_mask(const float* alphas, const int32_t* he
   ANGIO_REQUIRE(alphas && head_cnt && head_base && keep && kept_counts && t_end && alive && n_rays >= 0 && k0 >= 1 && k0 <= 32,
                 "angio_visibility_head_mask: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); visibility_head_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("visibility_head_mask_kernel"); visibility_head_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
       alphas, head_cnt, head_base, n_rays, k0, early_stop_eps, alpha_thre, keep, kept_counts, t_end, alive, alpha_thre_cap);
   return angio::finish_launch("angio_visibility_head_mask");
 }
@@ -268,7 +268,7 @@ extern "C" int angio_compact_head_tail(const uint8_t* keep_head, const int32_t* 
                     t_ends_out && n_rays >= 0,
                 "angio_compact_head_tail: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); compact_head_tail_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
+  angio::note_launch("compact_head_tail_kernel"); compact_head_tail_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(
       keep_head, head_cnt, head_base, head_t0, head_t1, keep_tail, tail_offsets, tail_t0, tail_t1, new_offsets, n_rays,
       capacity > 0 ? capacity : INT64_MAX, ray_idx_out, t_starts_out, t_ends_out);
   return angio::finish_launch("angio_compact_head_tail");
@@ -279,7 +279,7 @@ extern "C" int angio_compact_samples(const uint8_t* keep, const int32_t* offsets
                                      float* t_starts_out, float* t_ends_out, void* stream) {
   ANGIO_REQUIRE(offsets && new_offsets && n_rays >= 0, "angio_compact_samples: bad arguments");
   if (n_rays == 0) return 0;
-  angio::note_launch(); compact_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(keep, offsets, new_offsets, n_rays, t_starts, t_ends,
+  angio::note_launch("compact_kernel"); compact_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(keep, offsets, new_offsets, n_rays, t_starts, t_ends,
                                                                          capacity > 0 ? capacity : INT64_MAX, ray_idx_out, t_starts_out, t_ends_out);
   return angio::finish_launch("angio_compact_samples");
 }

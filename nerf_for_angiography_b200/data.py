@@ -99,11 +99,12 @@ def get_weighted_img(img, sampling_strategy="segmentation"):
     return w
 
 
-def make_volume(resolution=256, half_extent=100.0, kind="sdf", device="cuda", seed=0):
+def make_volume(resolution=256, half_extent=100.0, kind="sdf", device="cuda", seed=0, hu_mu_scale=0.03):
     """Attenuation volume mu[res,res,res] (indexed [x,y,z]) on the +-half_extent lattice.
 
     kind 'sdf': mu = rev_sigmoid(sdf, c1=2)           (phantomdata/helpers.py:93 convention, vessels ~1, air 0)
-    kind 'ct' : vessels + a soft-tissue ellipsoid, scaled to CT-like line integrals (configs 3-4)
+    kind 'ct' : vessels + a soft-tissue ellipsoid, scaled to CT-like line integrals
+    kind 'ct_hu': synthetic HU field through the reference's CT transfer function (configs 3-4)
     """
     caps = default_capsules(seed)
     lin = torch.linspace(-half_extent, half_extent, resolution, device=device)
@@ -116,6 +117,15 @@ def make_volume(resolution=256, half_extent=100.0, kind="sdf", device="cuda", se
         if kind == "ct":
             tissue = ((pts / torch.tensor([85.0, 70.0, 90.0], device=device)).norm(dim=-1) < 1.0).float()
             mu = 0.12 * mu + 0.0015 * tissue
+        elif kind == "ct_hu":
+            # CT-derived phantom (BASELINE config 3): a synthetic Hounsfield field -- air 0, a soft-tissue ellipsoid at
+            # ~1500 HU, contrast-filled vessels 3300 HU at the wall rising to 4000 HU on the centre line -- pushed through the
+            # reference's piecewise-linear transfer function (phantomdata/helpers.py:33-70), then scaled by `hu_mu_scale` per world
+            # unit so that line integrals over the +-100 box stay in the range of the reference's 100x100x(420 steps) CT geometry.
+            tissue = ((pts / torch.tensor([85.0, 70.0, 90.0], device=device)).norm(dim=-1) < 1.0).double()
+            core = (-sdf / 3.0).clamp(0.0, 1.0).double()
+            hu = mu.double() * (3300.0 + 700.0 * core) + (1.0 - mu.double()) * 1500.0 * tissue
+            mu = torch.from_numpy(transfer_func_ct(hu.cpu().numpy())).to(device=device, dtype=torch.float32) * hu_mu_scale
         elif kind == "sdf":
             mu = 0.08 * mu
         else:
@@ -276,7 +286,7 @@ def make_dataset(img_size=64, thetas=(0.0, 45.0, 90.0, 135.0), test_view=(135.0,
     pix = torch.empty((len(views), img_size, img_size), dtype=torch.float32, device=device)
     for v in range(len(views)):
         o, d = ops.raygen(cam, img_size, img_size, focal, view=v)
-        img = project(vol, o, d, near, far, n_proj_samples, half_extent, kind=kind)
+        img = project(vol, o, d, near, far, n_proj_samples, half_extent, kind="sdf" if kind == "sdf" else "ct")
         if kind == "sdf":                                        # per-image min-max normalisation (sdftoray.py:125-126)
             img = (img - img.min()) / (img.max() - img.min() + 1e-12)
         pix[v] = img.view(img_size, img_size)

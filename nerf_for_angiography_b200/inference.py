@@ -13,11 +13,12 @@ from .nerf.nerf_helpers_acc import acc_ray_marching, acc_render_volume_density
 @torch.no_grad()
 def render_projections(model, grid, scene_aabb, views, src_pt, img_width, img_height, focal_length, depth_samples_per_ray, near_thresh,
                        far_thresh, early_stop_eps=1e-2, alpha_thre=1e-3, binary_thresh=None, larm=0.0, translation=(0, 0, 0),
-                       gather=True):
+                       gather=True, shard=True):
     """Render novel views [(theta, phi), ...] through the hot path (visualization.py:315-354 for data_name == 'ct').
     Returns images [V, H, W] (and the 'binary' renders with sigma < binary_thresh zeroed when binary_thresh is given).
-    With torch.distributed initialised every rank renders a contiguous slice of the views."""
-    rank, ws = world()
+    With torch.distributed initialised every rank renders a contiguous slice of the views (shard=False: `views` is already
+    this rank's share and all of it is rendered here)."""
+    rank, ws = world() if shard else (0, 1)
     lo, hi = shard_range(len(views), rank, ws)
     dev = scene_aabb.device
     mats = np.stack([source_matrix(src_pt, th, ph, larm, translation) for th, ph in views[lo:hi]]) if hi > lo else np.zeros((0, 4, 4))

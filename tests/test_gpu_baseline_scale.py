@@ -1,0 +1,395 @@
+"""GPU parity tests at the sizes BASELINE.json names (configs 2 and 3): 128^3 occupancy grid, 512^2 x 61 views / 256^2 x 5 views,
+65 536 rays per batch drawn by the ray pool, grids thresholded from the phantom volume / random 5 % and 50 % / refreshed by
+>= 300 real training iterations, and the trained (thin) field.  Checked against the CPU oracle (oracle/march_ref.c,
+oracle/pipeline.py, oracle/cppn.py):
+
+  march            ray indices, segment offsets, t_starts, t_ends                       bit-exact   (65 536 rays)
+  visibility       lazy march == two-phase == evaluate-everything                      bit-exact   (65 536 rays, GPU vs GPU)
+  fp32 check mode  projection <= 1e-5; sample set: bounded symmetric difference        (4 096 rays; the oracle MLP runs on the CPU)
+  bf16             projection <= 1e-2 of the image scale / relative L2, trained field  (4 096 rays)
+  training step    loss and every gradient tensor vs the oracle's autograd             fp32 1e-4, bf16 stated per tensor
+
+Reference call sites: /root/reference/nerf/run_nerf_acc.py:197-198 (grid), :277 (ray draw), :284-307 (the iteration).
+"""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import cppn as ocppn, nerfacc_ref, pipeline  # noqa: E402
+
+RES = 128
+NEAR, FAR, STEPS = 1400.0, 1600.0, 300
+ROI = np.array([-100, -100, -100, 100, 100, 100], np.float32)
+CONFIGS = {"config3": dict(img=512, thetas=[6.0 * i for i in range(60)]),       # 61 views with the test view
+           "config2": dict(img=256, thetas=[0.0, 45.0, 90.0, 135.0])}            # 5 views
+
+
+@pytest.fixture(scope="module")
+def A():
+    import nerf_for_angiography_b200 as a
+    assert torch.cuda.is_available()
+    return a
+
+
+def _mdef(precision, L=4, H=128):
+    return {'num_early_layers': L, 'num_late_layers': 0, 'num_filters': H, 'num_input_channels': 3, 'num_output_channels': 1,
+            'num_input_channels_views': 0, 'use_bias': True, 'pos_enc': 'fourier', 'pos_enc_basis': 5, 'act_func': 'relu',
+            'fourier_sigma': 5, 'num_img': 1, 'device': torch.device("cuda"), 'precision': precision}
+
+
+_DATASETS = {}
+
+
+def _dataset(cfg):
+    """ray pool + phantom volume of a BASELINE config (cached per module run; the projections are rendered on the GPU)."""
+    if cfg not in _DATASETS:
+        from nerf_for_angiography_b200.data import make_dataset
+        c = CONFIGS[cfg]
+        _DATASETS[cfg] = make_dataset(img_size=c["img"], thetas=c["thetas"], test_view=(135.0, 135.0), kind="ct", volume_res=RES,
+                                      device="cuda", seed=0, weight_strategy="distance")
+    return _DATASETS[cfg]
+
+
+def _draw(pool, n, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    pool._seed_streams = {}
+    o, d, target = pool.sample(n, generator=g)
+    return o, d, target
+
+
+def _grid_fill(kind, volume):
+    rng = np.random.default_rng(11)
+    if kind == "phantom":          # cells whose attenuation is above the soft-tissue level: the vessel tree + its halo
+        return (volume.cpu().numpy() > 0.004)
+    if kind == "random5":
+        return rng.random((RES,) * 3) < 0.05
+    if kind == "random50":
+        return rng.random((RES,) * 3) < 0.5
+    raise ValueError(kind)
+
+
+def _oracle_march(o, d, binary):
+    tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, ROI, NEAR, FAR)
+    return nerfacc_ref.march(o, d, tmin, tmax, ROI, RES, binary, np.float32((FAR - NEAR) / STEPS))
+
+
+def _assert_march_equal(got, ref):
+    gi, g0, g1, goff = (x.cpu().numpy() for x in got)
+    ri, ts, te, off = ref
+    assert np.array_equal(goff.astype(np.int64), off), "segment offsets"
+    assert np.array_equal(gi.astype(np.int64), ri), "ray indices"
+    assert np.array_equal(g0, ts) and np.array_equal(g1, te), "interval ends"
+
+
+# ------------------------------------------------------------------------------------------------ march, 65 536 rays, 128^3
+@pytest.mark.parametrize("cfg,fill", [("config3", "phantom"), ("config3", "random5"), ("config3", "random50"), ("config2", "phantom"),
+                                      ("config2", "random50")])
+def test_march_bit_exact_at_config_scale(A, cfg, fill):
+    pool, info = _dataset(cfg)
+    binary = _grid_fill(fill, info["volume"])
+    o, d, _ = _draw(pool, 65536, seed=3)
+    got = A.ops.march(o, d, ROI, ROI, RES, torch.from_numpy(binary).cuda(), NEAR, FAR, (FAR - NEAR) / STEPS)
+    ref = _oracle_march(o.cpu().numpy(), d.cpu().numpy(), binary)
+    assert len(ref[0]) > 65536                                   # the batch really crosses the volume
+    _assert_march_equal(got, ref)
+    assert int(got[3][-1]) == len(ref[0])
+
+
+def _model_with(A, p, precision):
+    m = A.CPPN(_mdef(precision))
+    m.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    return m.to("cuda")
+
+
+@pytest.mark.parametrize("fill,bias_shift", [("random50", 0.0), ("phantom", -4.0), ("random5", -8.0)])
+def test_visibility_orders_agree_at_config_scale(A, fill, bias_shift):
+    """lazy marching == two-phase evaluation == evaluating every marched sample: the same kept samples, indices and offsets, bit
+    for bit, on 65 536 config-3 rays against a 128^3 grid (dense field: rays die in their head; thin field: nothing terminates)."""
+    pool, info = _dataset("config3")
+    binary = torch.from_numpy(_grid_fill(fill, info["volume"])).cuda()
+    o, d, _ = _draw(pool, 65536, seed=5)
+    p = ocppn.init_params(4, 128, "fourier", 5, 5.0, seed=3)
+    p["output_linear.0.bias"] = p["output_linear.0.bias"] + bias_shift
+    m = _model_with(A, p, "bf16"); m._ensure_flat()
+    packed = A.ops.mlp_pack(m._desc, m._flat)
+    step = (FAR - NEAR) / STEPS
+    ri, t0, t1, off = A.ops.march(o, d, ROI, ROI, RES, binary, NEAR, FAR, step)
+    kw = dict(rays_o=o, rays_d=d, ray_idx=ri, t_starts=t0, t_ends=t1)
+    full = A.ops.mlp_forward(m._desc, m._flat, packed, A.ops.OUT_ALPHA, A.ops.PREC_BF16, **kw)
+    e_ri, e_t0, e_t1, e_off, _ = A.ops.visibility_compact(full, off, t0, t1, 1e-2, 1e-4)
+    two, _ = A.ops.alphas_two_phase(m._desc, m._flat, packed, A.ops.PREC_BF16, o, d, ri, t0, t1, off, 1e-2, k0=32)
+    b = A.ops.visibility_compact(two, off, t0, t1, 1e-2, 1e-4)
+    assert b[0].equal(e_ri) and b[1].equal(e_t0) and b[2].equal(e_t1) and b[3].equal(e_off)
+    totals = torch.zeros(4, dtype=torch.int32, device="cuda")
+    l_ri, l_t0, l_t1, l_off = A.ops.march_filter_lazy(m._desc, m._flat, packed, A.ops.PREC_BF16, o, d, ROI, ROI, RES, binary, NEAR, FAR,
+                                                      step, 1e-2, 1e-4, k0=32, totals=totals)
+    n = int(l_off[-1])
+    assert n == e_ri.numel() > 0 and l_off.equal(e_off)
+    assert l_ri[:n].equal(e_ri) and l_t0[:n].equal(e_t0) and l_t1[:n].equal(e_t1)
+    assert totals.tolist()[1] == n and totals.tolist()[0] <= ri.numel()
+
+
+# ------------------------------------------------------------------------------------------------ trained state (>= 300 iterations)
+@pytest.fixture(scope="module")
+def trained(A):
+    """config 3 trained for 320 real iterations (bf16, sync-free loop, weighted ray draws): the model, both grids and a
+    fresh 65 536-ray batch."""
+    from nerf_for_angiography_b200.train import Trainer
+    pool, info = _dataset("config3")
+    torch.manual_seed(0)
+    model = A.CPPN(_mdef("bf16")).to("cuda")
+    tr = Trainer(model, pool, info["near"], info["far"], n_rays=65536, seed=0)
+    assert tr.sync_free and tr.lazy_march
+    losses = []
+    for i in range(320):
+        out = tr.step()
+        if i % 40 == 0 or i == 319:
+            losses.append(float(out["loss"]))
+    assert losses[-1] < 0.5 * losses[0], losses                   # it trains
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items() if k not in ("img1", "img2")}
+    binary = tr.acc_grid.binary.cpu().numpy().copy()
+    occs = tr.acc_grid.occs.cpu().numpy().copy()
+    o, d, target = _draw(pool, 65536, seed=9)
+    return dict(tr=tr, p=sd, binary=binary, occs=occs, o=o, d=d, target=target, losses=losses, info=info)
+
+
+def _oracle_grid(binary, occs):
+    og = nerfacc_ref.OccupancyGrid(ROI, RES)
+    og.binary = binary.copy(); og.occs[:] = occs
+    return og
+
+
+def _gpu_grid(A, binary, occs):
+    gg = A.OccupancyGrid(torch.tensor(ROI), RES, A.ContractionType.AABB).cuda()
+    gg._binary = torch.from_numpy(binary).cuda(); gg.occs.copy_(torch.from_numpy(occs))
+    return gg
+
+
+def test_trained_grid_march_bit_exact(A, trained):
+    """the grid after 320 iterations (EMA of sigmoid(MLP), refreshed 20 times): march of a fresh 65 536-ray batch vs the oracle"""
+    binary = trained["binary"]
+    assert 0 < binary.mean() <= 1.0
+    got = A.ops.march(trained["o"], trained["d"], ROI, ROI, RES, torch.from_numpy(binary).cuda(), NEAR, FAR, (FAR - NEAR) / STEPS)
+    _assert_march_equal(got, _oracle_march(trained["o"].cpu().numpy(), trained["d"].cpu().numpy(), binary))
+
+
+def test_trained_grid_refresh_matches_oracle(A, trained):
+    """one more refresh of the trained grid from fixed cells + jitter (post-warm-up branch: N/4 uniform + N/4 occupied cells),
+    occupancies from the fp32 check kernels vs the oracle MLP on the CPU: occs to 1e-6, binary identical where occs is not
+    within 1e-6 of the threshold"""
+    p = trained["p"]
+    og = _oracle_grid(trained["binary"], trained["occs"])
+    gg = _gpu_grid(A, trained["binary"], trained["occs"])
+    rng = np.random.default_rng(4)
+    cells = rng.permutation(RES ** 3)[:RES ** 3 // 8].astype(np.int64)            # duplicate-free (see oracle/nerfacc_ref.py)
+    jitter = rng.random((len(cells), 3), dtype=np.float32)
+    f = functools.partial(ocppn.cppn_forward, p, pos_enc="fourier", basis=5)
+    pipeline.acc_update_n_step(og, f, 320, occ_thre=1e-4, indices=cells, jitter=jitter)
+    m = _model_with(A, p, "fp32")
+    gg._update(320, lambda x: m.query(A.ops.OUT_SIGMA, points=x), occ_thre=1e-4, cells=torch.from_numpy(cells).cuda(),
+               jitter=torch.from_numpy(jitter).cuda())
+    occs = gg.occs.cpu().numpy()
+    assert np.max(np.abs(occs - og.occs)) <= 1e-6
+    thre = min(float(og.occs.mean(dtype=np.float32)), 1e-4)
+    clear = np.abs(og.occs - thre) > 1e-6
+    assert np.array_equal(gg.binary.cpu().numpy().reshape(-1)[clear], og.binary.reshape(-1)[clear])
+    assert np.isclose(gg.occs_mean_host, float(og.occs.mean(dtype=np.float32)), rtol=1e-5)
+
+
+def _subset(trained, n, seed=0):
+    sel = np.random.default_rng(seed).permutation(trained["o"].shape[0])[:n]
+    sel_t = torch.from_numpy(sel).cuda()
+    return trained["o"][sel_t].contiguous(), trained["d"][sel_t].contiguous(), trained["target"][sel_t].contiguous()
+
+
+def _sample_keys(ri, ts):
+    """(ray, t_start bits) -> one sortable int64 per sample"""
+    return (np.asarray(ri, np.int64) << 32) | np.asarray(ts, np.float32).reshape(-1).view(np.uint32).astype(np.int64)
+
+
+def test_trained_projection_fp32_and_bf16(A, trained):
+    """render_rays (run_nerf_acc.py:287-296) on the trained field + trained grid, 4 096 rays of a fresh batch:
+    fp32 check mode <= 1e-5 on the projection with the same kept samples up to threshold ties; bf16 <= 1e-2."""
+    p = trained["p"]
+    o, d, _ = _subset(trained, 4096)
+    og = _oracle_grid(trained["binary"], trained["occs"])
+    gg = _gpu_grid(A, trained["binary"], trained["occs"])
+    f = functools.partial(ocppn.cppn_forward, p, pos_enc="fourier", basis=5)
+    with torch.no_grad():
+        pix_ref, (ri, ts, te) = pipeline.render_rays(f, og, ROI, o.cpu().numpy(), d.cpu().numpy(), STEPS, NEAR, FAR, 1e-2, 1e-4)
+    pix_ref = pix_ref.numpy()
+    assert len(ri) > 10 * 4096 and pix_ref.max() <= 1.0                              # thin field: long ray segments survive
+    roi_t = torch.tensor(ROI).cuda()
+    for prec in ("fp32", "bf16"):
+        m = _model_with(A, p, prec)
+        with torch.no_grad():
+            pix, (gi, g0, g1) = A.render_rays(m, gg, roi_t, o, d, STEPS, NEAR, FAR, 1e-2, 1e-4)
+        pix = pix.cpu().numpy()
+        if prec == "fp32":
+            # same kept samples except visibility decisions within rounding of a threshold: bounded symmetric difference
+            a, b = _sample_keys(gi.cpu().numpy(), g0.cpu().numpy()), _sample_keys(ri, ts)
+            sym = np.setxor1d(a, b).size
+            assert sym <= max(4, int(2e-5 * len(ri))), (sym, len(ri))
+            common, ia, ib = np.intersect1d(a, b, return_indices=True)
+            assert np.array_equal(g1.cpu().numpy().reshape(-1)[ia], te.reshape(-1)[ib])
+            assert np.max(np.abs(pix - pix_ref)) <= 1e-5, np.max(np.abs(pix - pix_ref))
+        else:
+            err = np.abs(pix - pix_ref)
+            assert err.max() <= 1e-2 * pix_ref.max(), err.max()
+            assert np.linalg.norm(pix - pix_ref) / np.linalg.norm(pix_ref) <= 1e-2
+            bright = pix_ref > 0.1
+            assert np.max(err[bright] / pix_ref[bright]) <= 1e-2, np.max(err[bright] / pix_ref[bright])
+
+
+def _oracle_step(p, og, o, d, target):
+    params = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    f = functools.partial(ocppn.cppn_forward, params, pos_enc="fourier", basis=5)
+    pix, (ri, ts, te) = pipeline.render_rays(f, og, ROI, o, d, STEPS, NEAR, FAR, 1e-2, 1e-4)
+    loss = torch.nn.functional.mse_loss(pix, torch.from_numpy(target))
+    loss.backward()
+    order = ["fourier_coefficients"] + [f"early_pts_layers.{2 * i}.{w}" for i in range(5) for w in ("weight", "bias")] + \
+        ["output_linear.0.weight", "output_linear.0.bias"]
+    return float(loss), {k: params[k].grad.numpy().copy() for k in order}, order, len(ri)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_trained_training_step_vs_oracle_autograd(A, trained, precision):
+    """One reference iteration (run_nerf_acc.py:284-307) on the trained state, 4 096 rays: loss and EVERY gradient tensor against
+    the oracle's torch autograd.  fp32 check path: 1e-5 / 1e-4.  bf16 tcgen05 path (forward, dgrad, wgrad in bf16 with fp32
+    accumulation): loss 5e-3, gradient tensors <= 4e-2 relative L2 each and <= 2.5e-2 over the whole flat gradient (measured: 2.2e-2 /
+    1.4e-2)."""
+    from nerf_for_angiography_b200.data import RayPool
+    from nerf_for_angiography_b200.train import Trainer
+    p = trained["p"]
+    o, d, target = _subset(trained, 4096, seed=1)
+    og = _oracle_grid(trained["binary"], trained["occs"])
+    loss_ref, gref, order, n_ref = _oracle_step(p, og, o.cpu().numpy(), d.cpu().numpy(), target.cpu().numpy())
+    m = _model_with(A, p, precision)
+    dummy = RayPool(torch.eye(4, dtype=torch.float64).cuda()[None], torch.zeros(1, 2, 2).cuda(), 1.0)
+    tr = Trainer(m, dummy, NEAR, FAR, n_rays=4096, vessel_grid=False)
+    tr.acc_grid = _gpu_grid(A, trained["binary"], trained["occs"])
+    tr.n_iter = 1                                                  # no grid refresh in this step
+    out = tr.step(rays=(o, d, target))
+    got = tr.grad[:-1].cpu().numpy()
+    flat_ref = np.concatenate([gref[k].reshape(-1) for k in order])
+    assert abs(out["n_samples"] - n_ref) <= max(4, int(1e-3 * n_ref))
+    if precision == "fp32":
+        assert np.isclose(float(out["loss"]), loss_ref, rtol=1e-5)
+        assert np.max(np.abs(got - flat_ref)) <= 1e-4 * np.abs(flat_ref).max()
+        return
+    assert np.isclose(float(out["loss"]), loss_ref, rtol=5e-3), (float(out["loss"]), loss_ref)
+    off, worst = 0, {}
+    for k in order:
+        n = gref[k].size
+        g, r = got[off:off + n], gref[k].reshape(-1)
+        worst[k] = float(np.linalg.norm(g - r) / max(np.linalg.norm(r), 1e-12))
+        off += n
+    total = float(np.linalg.norm(got - flat_ref) / np.linalg.norm(flat_ref))
+    print("bf16 gradient relative L2 vs oracle autograd:", {k: round(v, 4) for k, v in worst.items()}, "flat:", round(total, 4))
+    assert total <= 2.5e-2, total
+    assert max(worst.values()) <= 4e-2, worst
+
+
+# ------------------------------------------------------------------------------------------------ third-party cross-check hook
+def test_oracle_march_against_installed_nerfacc():
+    """nerfacc is a third-party dependency the reference does not vendor or pin.  Where a nerfacc 0.3.x build is
+    importable next to a GPU, the oracle's restatement of its marcher / visibility filter is compared with the library itself;
+    everywhere else (this image: not installed, no network) the test is skipped and parity stays 'unpinned' (DESIGN.md)."""
+    nerfacc = pytest.importorskip("nerfacc")
+    if not hasattr(nerfacc, "OccupancyGrid") or not hasattr(nerfacc, "ray_marching"):
+        pytest.skip("nerfacc %s does not expose the 0.3.x API the reference uses" % getattr(nerfacc, "__version__", "?"))
+    rng = np.random.default_rng(0)
+    res = 64
+    binary = rng.random((res,) * 3) < 0.3
+    R = 4096
+    o = np.tile(np.array([[0, 0, 1500.0]], np.float32), (R, 1)) + rng.normal(0, 1, (R, 3)).astype(np.float32)
+    d = np.concatenate([rng.uniform(-0.06, 0.06, (R, 2)), -np.ones((R, 1))], axis=1).astype(np.float32)
+    grid = nerfacc.OccupancyGrid(roi_aabb=torch.tensor(ROI), resolution=res, contraction_type=nerfacc.ContractionType.AABB).cuda()
+    grid._binary = torch.from_numpy(binary).cuda()
+    with torch.no_grad():
+        ri, ts, te = nerfacc.ray_marching(torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda(), scene_aabb=torch.tensor(ROI).cuda(),
+                                          grid=grid, near_plane=NEAR, far_plane=FAR, render_step_size=(FAR - NEAR) / STEPS)
+    tmin, tmax = nerfacc_ref.ray_aabb_intersect(o, d, ROI, NEAR, FAR)
+    ri_o, ts_o, te_o, off = nerfacc_ref.march(o, d, tmin, tmax, ROI, res, binary, np.float32((FAR - NEAR) / STEPS))
+    mism = int(len(ri_o) != len(ri))
+    if not mism:
+        mism = int((ri.cpu().numpy() != ri_o).sum() + (ts.cpu().numpy().reshape(-1) != ts_o).sum() + (te.cpu().numpy().reshape(-1) != te_o).sum())
+    print(f"nerfacc {getattr(nerfacc, '__version__', '?')}: {len(ri)} samples from the library, {len(ri_o)} from the oracle, {mism} mismatches")
+    assert mism == 0
+
+
+# ------------------------------------------------------------------------------------------------ sample_pixel_rays, per ray
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(z):
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def _race_keys(seed, n_pool, w):
+    """the sampler's exponential-race keys (csrc/sampler.cu: counter-based hash -> Exp(1) variate / weight), in float64"""
+    with np.errstate(over="ignore"):
+        i = np.arange(1, n_pool + 1, dtype=np.uint64)
+        h = _mix64(np.uint64(seed) + np.uint64(0x9E3779B97F4A7C15) * i)
+    hi = (h >> np.uint64(40)).astype(np.float64)
+    lo = ((h >> np.uint64(16)) & np.uint64(0xFFFFFF)).astype(np.float64)
+    v = (hi + (lo + 0.5) / 16777216.0) / 16777216.0
+    return -np.log1p(-v) / w
+
+
+def test_sampler_selects_exactly_the_smallest_race_keys(A):
+    """Check mode for sample_pixel_rays (nerf_helpers.py:137-150): the sampler's random keys come from a counter-based hash
+    of (seed, ray id), so numpy can draw the SAME keys; the selected set must be exactly the n smallest keys -- the sequential
+    weighted draw of DataFrame.sample(n, weights) in its exponential-race form -- per ray, not per view.  (fp32 keys on the
+    device vs float64 here: rays whose key is within 1e-4 relative of the n-th smallest may land on either side.)"""
+    rng = np.random.default_rng(2)
+    for n_pool, n in ((200_000, 4096), (1_000_000, 65536), (5000, 5000 // 3)):
+        w = (rng.random(n_pool) ** 3 + 1e-4).astype(np.float32)
+        w[rng.random(n_pool) < 0.1] = 0.0                                  # unsamplable rays
+        seed = int(rng.integers(0, 2 ** 62))
+        wd = w.astype(np.float64)
+        ids, status = A.ops.sample_without_replacement(n, n_pool, torch.from_numpy(w).cuda(), float(wd.sum()), float((wd ** 2).sum()), seed,
+                                                       torch.device("cuda"))
+        assert status.tolist()[1] == 0
+        got = np.sort(ids.cpu().numpy())
+        assert len(np.unique(got)) == n
+        with np.errstate(divide="ignore"):
+            keys = np.where(w > 0, _race_keys(seed, n_pool, wd), np.inf)
+        order = np.argsort(keys, kind="stable")
+        kth = keys[order[n - 1]]
+        sure_in = np.flatnonzero(keys < kth * (1 - 1e-4))
+        sure_out = np.flatnonzero(keys > kth * (1 + 1e-4))
+        assert np.isin(sure_in, got).all(), "a ray with one of the n smallest keys is missing"
+        assert not np.isin(sure_out, got).any(), "a ray with a larger key was drawn"
+        assert len(sure_in) >= n - 64
+
+
+def test_sampler_inclusion_frequency_per_ray(A):
+    """Per-ray inclusion frequencies of the weighted draw without replacement against numpy's sequential sampler (what pandas
+    calls): 4 096 rays with weights spanning three decades, 512 per draw, 3 000 draws each side; every ray within 6 sigma."""
+    n_pool, n, T = 4096, 512, 3000
+    rng = np.random.default_rng(5)
+    w = (10.0 ** rng.uniform(-3, 0, n_pool)).astype(np.float32)
+    wd = w.astype(np.float64)
+    wt = torch.from_numpy(w).cuda()
+    counts = torch.zeros(n_pool, device="cuda")
+    for t in range(T):
+        ids, _ = A.ops.sample_without_replacement(n, n_pool, wt, float(wd.sum()), float((wd ** 2).sum()), 1000003 * t + 17, torch.device("cuda"))
+        counts[ids] += 1
+    f_gpu = counts.cpu().numpy() / T
+    ref = np.zeros(n_pool)
+    p = wd / wd.sum()
+    for t in range(T):
+        ref[rng.choice(n_pool, n, replace=False, p=p)] += 1
+    f_ref = ref / T
+    pi = 0.5 * (f_gpu + f_ref)
+    sigma = np.sqrt(2.0 * np.maximum(pi * (1 - pi), 1.0 / T) / T)
+    z = np.abs(f_gpu - f_ref) / sigma
+    assert z.max() <= 6.0, (z.max(), int(z.argmax()))
+    assert abs(f_gpu.sum() - n) < 1e-6 and np.corrcoef(f_gpu, f_ref)[0, 1] > 0.995

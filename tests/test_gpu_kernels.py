@@ -396,9 +396,14 @@ def test_sampler_edge_cases(A):
     assert some.unique().numel() == 100 and bool((w.view(-1)[some] > 0).all())
     allpos = pool.sample_ids(300, generator=g)
     assert allpos.sort().values.equal(pos.sort().values) and pool.last_status.tolist()[1] == 0
-    # asking for more rays than have positive weight cannot be satisfied: the status flag says so instead of returning garbage silently
-    pool.sample_ids(301, generator=g)
-    assert pool.last_status.tolist()[1] == 1
+    # asking for more rays than have positive weight cannot be satisfied: the pool refuses (numpy / pandas raise here too) ...
+    with pytest.raises(ValueError):
+        pool.sample_ids(301, generator=g)
+    # ... and the kernels themselves flag the failed draw and leave VALID ids behind (the gather that follows reads them
+    # before any host code has looked at the status)
+    wf = w.reshape(-1).contiguous()
+    ids, status = A.ops.sample_without_replacement(301, V * H * W, wf, float(wf.sum()), float((wf.double() ** 2).sum()), 7, wf.device)
+    assert status.tolist()[1] == 1 and int(ids.min()) == 0 and int(ids.max()) == 0
 
 
 def test_sampler_with_the_reference_weight_images(A):

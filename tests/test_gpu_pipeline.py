@@ -171,10 +171,14 @@ def test_render_rays_vs_oracle(A, precision, L, H, pos_enc):
     assert gi.dtype == torch.int64 and g0.shape == (len(gi), 1)
     pix, pix_ref = pix.cpu().numpy(), pix_ref.numpy()
     if precision == "fp32":
-        # sample set: identical up to visibility decisions that sit within 1 ulp of the threshold
-        assert abs(len(gi) - len(ri)) <= max(2, int(1e-4 * len(ri)))
-        if len(gi) == len(ri):
-            assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(g0.cpu().numpy(), ts) and np.array_equal(g1.cpu().numpy(), te)
+        # sample set: identical up to visibility decisions that sit within rounding of a threshold -- the symmetric difference of
+        # the (ray, t_start) sets is bounded, and every sample both sides kept has bit-identical interval ends
+        key = lambda r, t: (np.asarray(r, np.int64) << 32) | np.asarray(t, np.float32).reshape(-1).view(np.uint32).astype(np.int64)
+        a, b = key(gi.cpu().numpy(), g0.cpu().numpy()), key(ri, ts)
+        assert np.setxor1d(a, b).size <= max(2, int(1e-4 * len(ri))), np.setxor1d(a, b).size
+        _, ia, ib = np.intersect1d(a, b, return_indices=True)
+        assert len(ia) >= len(ri) - max(2, int(1e-4 * len(ri)))
+        assert np.array_equal(g1.cpu().numpy().reshape(-1)[ia], te.reshape(-1)[ib])
         assert np.max(np.abs(pix - pix_ref)) <= 1e-5                 # fp32 check mode: <= 1e-5 on the projection
     else:
         # bf16 MLP: <= 1e-2 relative error on the projection, measured against the image scale (pixels live in [0, 1])
