@@ -355,7 +355,8 @@ def main():
     sync_all()
     every = max(1, args.steps // 8)
     window_ms, step_totals, launches = [], [], 0
-    wait0 = tr.peer.wait_stats.clone() if tr.peer is not None else None
+    if tr.peer is not None:
+        tr.peer.wait_stats.zero_()
     for rep in range(args.repeats):
         tr.restore(snap)
         last = rep == args.repeats - 1
@@ -387,7 +388,7 @@ def main():
     last_loss = float(body.out["loss"])
     wait = None
     if tr.peer is not None:
-        ws = (tr.peer.wait_stats - wait0).tolist()
+        ws = tr.peer.wait_stats.tolist()
         wt = torch.tensor([ws[0] / max(ws[1], 1) * 1e-3, ws[2] * 1e-3], dtype=torch.float64, device=dev)     # mean / longest wait of this rank, us
         mx, mean = wt.clone(), wt.clone()
         torch.distributed.all_reduce(mx, op=torch.distributed.ReduceOp.MAX)

@@ -137,6 +137,11 @@ __device__ __forceinline__ void trace_event(int kind, int slot, int stage, int r
   if (g_trace != nullptr && blockIdx.x == 0 && round < 16) g_trace[((round * 8 + stage) * 2 + slot) * 4 + kind] = clock64();
 }
 
+// three-slot kernel: cell [round][stage][slot][kind], 16 rounds x 8 stages x 4 slots x 4 kinds
+__device__ __forceinline__ void trace_event3(int kind, int slot, int stage, int round) {
+  if (g_trace != nullptr && blockIdx.x == 0 && round < 16) g_trace[((round * 8 + stage) * 4 + slot) * 4 + kind] = clock64();
+}
+
 struct __align__(8) PipeBarriers {
   uint64_t w_ready;
   uint64_t a_ready[2];
@@ -549,7 +554,7 @@ struct __align__(8) PipeBarriers3 {
 template <bool LAST>
 __device__ __forceinline__ float bias_relu_32(const uint32_t (&r)[32], const float* __restrict__ bias, const float* __restrict__ w_out,
                                               uint32_t (&pk)[16]) {
-  float dot0 = 0.0f, dot1 = 0.0f;
+  float dot0 = 0.0f;     // ONE chain in column order: the same summation order as the two-slot / training forward (bit-identical logits)
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) {
     const float4 b0 = *reinterpret_cast<const float4*>(bias + 4 * jj);
@@ -557,14 +562,14 @@ __device__ __forceinline__ float bias_relu_32(const uint32_t (&r)[32], const flo
     const float2 u1 = __fadd2_rn(make_float2(__uint_as_float(r[4 * jj + 2]), __uint_as_float(r[4 * jj + 3])), make_float2(b0.z, b0.w));
     if (LAST) {
       const float4 w0 = *reinterpret_cast<const float4*>(w_out + 4 * jj);
-      dot0 = fmaf(fmaxf(u0.x, 0.f), w0.x, dot0); dot1 = fmaf(fmaxf(u0.y, 0.f), w0.y, dot1);
-      dot0 = fmaf(fmaxf(u1.x, 0.f), w0.z, dot0); dot1 = fmaf(fmaxf(u1.y, 0.f), w0.w, dot1);
+      dot0 = fmaf(fmaxf(u0.x, 0.f), w0.x, dot0); dot0 = fmaf(fmaxf(u0.y, 0.f), w0.y, dot0);
+      dot0 = fmaf(fmaxf(u1.x, 0.f), w0.z, dot0); dot0 = fmaf(fmaxf(u1.y, 0.f), w0.w, dot0);
     } else {
       pk[2 * jj] = pack_bf16x2_relu(u0.x, u0.y);
       pk[2 * jj + 1] = pack_bf16x2_relu(u1.x, u1.y);
     }
   }
-  return dot0 + dot1;
+  return dot0;
 }
 
 template <int OUT_MODE>
@@ -575,13 +580,13 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
   __shared__ float s_dot[kSlots3][kTile];                                  // output layer: column-half 1's partial dot products
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
-  int64_t n = in.n;
-  if (in.n_dev) { const int64_t nd = *in.n_dev; n = nd < n ? nd : n; }     // device-resident count (sync-free marcher -> MLP)
-  const int64_t n_tiles = (n + kTile - 1) / kTile;
+  int n = (int)in.n;                                                       // < 2^31 (checked by the launcher): 32-bit indices save registers
+  if (in.n_dev) { const int nd = *in.n_dev; n = nd < n ? nd : n; }         // device-resident count (sync-free marcher -> MLP)
+  const int n_tiles = (n + kTile - 1) / kTile;
   // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...; slot = j % 3.  Every slot runs the same number of rounds (the
   // strict MMA rotation needs that); tiles past the end are computed on zero inputs and not stored.
-  const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t rounds = (my_tiles + kSlots3 - 1) / kSlots3;
+  const int my_tiles = (n_tiles > (int)blockIdx.x) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int rounds = (my_tiles + kSlots3 - 1) / kSlots3;
   if (threadIdx.x == 0) {
     mbar_init(&bars.w_ready, 1);
     for (int s = 0; s < kSlots3; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); }
@@ -604,7 +609,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     const int k0_steps = P.k0_pad / 16;
     uint32_t m = 0;                                    // MMA sequence number: A from region m % 4, D into region (m + 3) % 4
     uint32_t phase = 0;                                // all slots flip together: one full rotation per (round, stage)
-    for (int64_t rd = 0; rd < rounds; ++rd) {
+    for (int rd = 0; rd < rounds; ++rd) {
       for (int st = 0; st < n_stages; ++st) {
         const uint32_t wbase = smem_base + w_offset(st);
 #pragma unroll
@@ -612,6 +617,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
           mbar_wait(&bars.a_ready[s], phase);
           fence_after_sync();
           if (lane == 0) {
+            trace_event3(0, s, st, rd);
             const uint32_t a_reg = (m & 3u) * 128u, d_reg = ((m + 3u) & 3u) * 128u;
             if (st == 0) {
               for (int k = 0; k < k0_steps; ++k)
@@ -623,6 +629,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
                        k > 0);
             }
             mma_commit(&bars.acc_ready[s]);
+            trace_event3(1, s, st, rd);
           }
           __syncwarp();
         }
@@ -643,8 +650,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     const int pair_bar = 1 + g * 4 + q;           // named barrier shared by the two column-half warps of this row quadrant
     const int nb = 3 * P.basis;
     uint32_t phase = 0;
-    auto fetch = [&](int64_t jt, float (&xx)[3], float& dtt, bool& vv, int64_t& idx) {
-      int64_t ii = (blockIdx.x + jt * gridDim.x) * kTile + row;
+    auto fetch = [&](int jt, float (&xx)[3], float& dtt, bool& vv, int& idx) {
+      int ii = ((int)blockIdx.x + jt * (int)gridDim.x) * kTile + row;
       vv = (jt < my_tiles) && (ii < n);
       xx[0] = xx[1] = xx[2] = 0.f;
       dtt = 0.f;
@@ -667,15 +674,15 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     };
     float xn[3], dtn;
     bool vn;
-    int64_t in_;
+    int in_;
     uint32_t f0[8], f1[8];
     fetch(g, xn, dtn, vn, in_);
     encode(xn, f0, f1);
     store_features((uint32_t)g * 128u, f0, f1);           // MMA number g reads region g
     signal_a_ready(&bars.a_ready[g], lane);
-    for (int64_t rd = 0; rd < rounds; ++rd) {
-      const int64_t j = rd * kSlots3 + g;
-      const int64_t i = in_;                      // where this row's output goes
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int j = rd * kSlots3 + g;
+      const int i = in_;                          // where this row's output goes
       const bool valid = vn;
       const float dt = dtn;
       const bool more = rd + 1 < rounds;
@@ -687,6 +694,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
+        if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(2, g, l, rd);
         const float* bias = consts + l * 128 + h * 64;
         uint32_t r[32], pk[16];
         tmem_ld32(reg, r);
@@ -698,6 +706,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         bias_relu_32<false>(r, bias + 32, nullptr, pk);
         tmem_st16(reg + 16, pk);
         signal_a_ready(&bars.a_ready[g], lane);
+        if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(3, g, l, rd);
       }
       // ---- last hidden layer + output layer: logit = w_out . relu(z_{L+1}) + b_out on the CUDA cores, in fp32
       {
@@ -707,6 +716,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
+        if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(2, g, l, rd);
         const float* bias = consts + l * 128 + h * 64;
         uint32_t r[32], pk[16];
         tmem_ld32(reg, r);
@@ -719,6 +729,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         if (more) {
           store_features(((m + 3u) & 3u) * 128u, f0, f1);
           signal_a_ready(&bars.a_ready[g], lane);
+          if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(3, g, l, rd);
         }
         dot += bias_relu_32<true>(r, bias + 32, w_out + 32, pk);
         // the h = 1 warp hands its half of the dot product to the h = 0 warp of the same row quadrant
@@ -1176,6 +1187,7 @@ static int launch_fwd3(const TcPlan& P, const void* packed, const angio_samples&
   const size_t smem = (size_t)P.total_bytes + 1024;
   static size_t cached = 0;
   if (int rc = ensure_smem(mlp_fwd3_tc_kernel<MODE>, smem, &cached)) return rc;
+  if (in.n >= ((int64_t)1 << 31) - (int64_t)kTile * 1024) { set_error("mlp_fwd3_tc_kernel: at most 2^31 samples per launch"); return ANGIO_ERR_INVALID_ARG; }
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
   int grid = sm_count();
   if (n_tiles < grid) grid = (int)n_tiles;

@@ -96,6 +96,7 @@ class Trainer:
             self.sync_free = bool(flag.item())
         # draw + march the next batch under the gradient all-reduce (sync-free mode); ANGIO_PREFETCH=0 keeps the plain order
         self.prefetch = os.environ.get("ANGIO_PREFETCH", "1") != "0"
+        self.shard_grid = os.environ.get("ANGIO_SHARD_GRID", "1") != "0"
         self._prefetched = None
         self._march_calls = 0
         # visibility pass with early ray termination (bf16 path): number of leading samples per ray evaluated before the rays
@@ -132,7 +133,25 @@ class Trainer:
 
     # ------------------------------------------------------------------ pieces
     def _occ_eval(self, x):
-        return ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x)
+        """occ_eval_fn of acc_update_n_step (sigma at the jittered cell points).  Data-parallel runs SHARD the refresh: every rank
+        draws the same cells / jitter (same generator), evaluates a contiguous 1/world slice of them and all-gathers the
+        occupancies (the per-sample result of the kernel does not depend on which rank or tile computed it, so every rank
+        ends up with bit-identical grids).  ANGIO_SHARD_GRID=0: every rank evaluates every cell."""
+        n = x.shape[0]
+        if self.world == 1 or not self.shard_grid or n < self.world:
+            return ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x)
+        chunk = (n + self.world - 1) // self.world
+        lo = min(self.rank * chunk, n)
+        hi = min(lo + chunk, n)
+        full = self.pool_bufs.typed("occ_gather", chunk * self.world, torch.float32, self.dev)
+        mine = full[self.rank * chunk:(self.rank + 1) * chunk]
+        if hi > lo:
+            ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x[lo:hi],
+                            out=mine[:hi - lo])
+        if hi - lo < chunk:
+            mine[hi - lo:].zero_()
+        torch.distributed.all_gather_into_tensor(full, mine.clone(), group=self.pg)
+        return full[:n]
 
     def update_grids(self):
         """acc_update_n_step for both grids (run_nerf_acc.py:285-286)."""

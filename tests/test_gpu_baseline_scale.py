@@ -5,7 +5,7 @@ oracle/pipeline.py, oracle/cppn.py):
 
   march            ray indices, segment offsets, t_starts, t_ends                       bit-exact   (65 536 rays)
   visibility       lazy march == two-phase == evaluate-everything                      bit-exact   (65 536 rays, GPU vs GPU)
-  fp32 check mode  projection <= 1e-5; sample set: bounded symmetric difference        (4 096 rays; the oracle MLP runs on the CPU)
+  fp32 check mode  projection <= 1e-5 on rays with identical kept samples; sample set: bounded symmetric difference (4 096 rays)
   bf16             projection <= 1e-2 of the image scale / relative L2, trained field  (4 096 rays)
   training step    loss and every gradient tensor vs the oracle's autograd             fp32 1e-4, bf16 stated per tensor
 
@@ -236,7 +236,15 @@ def test_trained_projection_fp32_and_bf16(A, trained):
             assert sym <= max(4, int(2e-5 * len(ri))), (sym, len(ri))
             common, ia, ib = np.intersect1d(a, b, return_indices=True)
             assert np.array_equal(g1.cpu().numpy().reshape(-1)[ia], te.reshape(-1)[ib])
-            assert np.max(np.abs(pix - pix_ref)) <= 1e-5, np.max(np.abs(pix - pix_ref))
+            # rays whose kept samples are identical: <= 1e-5.  A sample that sits within rounding of alpha_thre = 1e-4 and is kept
+            # on one side only multiplies its pixel by (1 - 1e-4): those few rays are bounded by 1.5e-4 per differing sample.
+            odd = np.setxor1d(a, b) >> 32
+            same = np.ones(len(pix), bool); same[odd] = False
+            err = np.abs(pix - pix_ref)
+            assert err[same].max() <= 1e-5, err[same].max()
+            if len(odd):
+                rays, cnt = np.unique(odd, return_counts=True)
+                assert np.all(err[rays] <= 1.5e-4 * cnt + 1e-5), (err[rays], cnt)
         else:
             err = np.abs(pix - pix_ref)
             assert err.max() <= 1e-2 * pix_ref.max(), err.max()

@@ -49,11 +49,29 @@ def main():
     ep = float((p - p_ref).abs().max())
     kept = torch.tensor([float(out["n_samples"])], device=dev)
     torch.distributed.all_reduce(kept)
+    # sharded occupancy-grid refresh (this step refreshed both grids: iteration 0): every rank evaluated 1/world of the cells and
+    # all-gathered the occupancies -- the grids must be bit-identical to the 1-rank refresh, on every rank
+    grids_equal = all(bool(a.occs.equal(b.occs)) and bool(a.binary.equal(b.binary))
+                      for a, b in ((tr.acc_grid, ref.acc_grid), (tr.vessel_acc_grid, ref.vessel_acc_grid)))
+    ge = torch.tensor([1.0 if grids_equal else 0.0], device=dev)
+    torch.distributed.all_reduce(ge, op=torch.distributed.ReduceOp.MIN)
+    # a second step: replicas must stay bit-identical (same summation order on every rank)
+    out2 = tr.step(rays=(o[sl].contiguous(), d[sl].contiguous(), t[sl].contiguous()))
+    pmin, pmax = tr.flat.clone(), tr.flat.clone()
+    torch.distributed.all_reduce(pmin, op=torch.distributed.ReduceOp.MIN)
+    torch.distributed.all_reduce(pmax, op=torch.distributed.ReduceOp.MAX)
+    replicas_identical = bool(pmin.equal(pmax))
     if rank == 0:
         print(f"world={world} rays/rank={R}: max |grad - grad_1rank| / max|grad| = {eg:.2e}, max |param - param_1rank| = {ep:.2e}, "
               f"kept samples {int(kept.item())} vs {ref.last['n_samples']} (1 rank)")
         assert int(kept.item()) == ref.last["n_samples"]
         assert eg <= 1e-5 and ep <= 2.1e-4, (eg, ep)
+        print(f"sharded grid refresh (shard_grid={tr.shard_grid}): grids bit-identical to the 1-rank refresh on every rank: {bool(ge.item())}; "
+              f"parameters bit-identical across ranks after 2 steps: {replicas_identical}")
+        assert bool(ge.item()) and replicas_identical
+        if tr.peer is not None:
+            ws = tr.peer.wait_stats.tolist()
+            print(f"peer all-reduce wait (rank 0): {ws[0] / max(ws[1], 1) * 1e-3:.1f} us mean over {ws[1]} steps, longest {ws[2] * 1e-3:.1f} us")
         print("DP EQUIVALENCE OK", "(gradient exchange: NVLink peer memory, fused into Adam)" if tr.peer is not None else "(NCCL all_reduce)")
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
