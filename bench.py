@@ -47,8 +47,7 @@ WORKLOADS = {
     "config3": dict(img=512, thetas=[6.0 * i for i in range(60)], rays=65536, vol=256, kind="ct_hu", L=4, H=128, enc="fourier"),
     "config2": dict(img=256, thetas=[0.0, 45.0, 90.0, 135.0], rays=65536, vol=256, kind="ct", L=4, H=128, enc="fourier"),
     # BASELINE configs[3]: 1024^2 x 120 views, 8x256 MLP
-    "config4": dict(img=1024, thetas=[3.0 * i for i in range(120)], rays=131072, vol=256, kind="ct_hu", L=8, H=256, enc="fourier",
-                    precision="fp32"),
+    "config4": dict(img=1024, thetas=[3.0 * i for i in range(120)], rays=131072, vol=256, kind="ct_hu", L=8, H=256, enc="fourier"),
     # BASELINE configs[4]: inference -- 360 novel views at 512^2 + a 512^3 volume query, trained 4x128 model + grid
     "config5": dict(img=512, thetas=[6.0 * i for i in range(60)], rays=65536, vol=256, kind="ct_hu", L=4, H=128, enc="fourier",
                     inference=dict(views=360, views_per_step=4, volume=512)),
@@ -201,7 +200,7 @@ def build_rooflines(timeline, cnt, w, peaks, world):
     img_bytes = ((3 + 6 * 5 + 15) // 16 * 16 + (w["L"] + 1) * H) * 2            # a_0 .. a_{L+1} bf16 tile images per sample
     delta_bytes = (w["L"] + 1) * H * 2
     spec = {   # kernel: (bound, algorithmic work per step, unit, note)
-        "mlp_fwd_tc_kernel<ALPHA>": ("tensor", flop * marched, "no-grad visibility pass: 2*MAC per evaluated sample"),
+        "mlp_fwd_tc_kernel<ALPHA>": ("tensor", flop * cnt.get("evals", marched), "no-grad visibility pass: 2*MAC per evaluated sample"),
         "mlp_fwd_tc_kernel<LOGIT,train>": ("tensor", flop * kept, f"training forward, 2*MAC per kept sample; also streams {img_bytes + 16 * (w['L'] + 1)} B/sample of saved tile images"),
         "mlp_dgrad_tc_kernel": ("tensor", flop * kept, f"data-gradient chain, 2*MAC per kept sample; also streams {delta_bytes} B/sample of delta images"),
         "mlp_wgrad_tc_kernel": ("tensor", flop * kept, f"weight gradients, 2*MAC per kept sample; streams {img_bytes + delta_bytes} B/sample (HBM-bound by design)"),
@@ -219,6 +218,14 @@ def build_rooflines(timeline, cnt, w, peaks, world):
         "adam_kernel": ("hbm", 28 * cnt["params"], "16 B/param in, 12 B/param out"),
         "adam_allreduce_kernel": ("nvlink-latency", (4 * world + 24) * cnt["params"], "world x 4 B/param peer reads + Adam"),
     }
+    for a, b in (("mlp_fwd_tc_kernel", "mlp256_fwd_kernel"), ("mlp_dgrad_tc_kernel", "mlp256_dgrad_kernel"), ("mlp_wgrad_tc_kernel", "mlp256_wgrad_kernel"),
+                 ("outgrad_partial_kernel", "outgrad256_partial_kernel")):          # the width-256 kernel family: same accounting
+        for k in [k for k in spec if k.startswith(a)]:
+            spec[k.replace(a, b)] = spec[k]
+    if tail == 0.0:       # one-sync path: full march (count + write) and a two-phase visibility pass over it
+        spec["march_write_kernel"] = ("hbm", 12 * marched + 4 * R, "12 B/sample out")
+        spec["visibility_mask_kernel"] = ("hbm", 5 * marched + 8 * R, "4 B/sample in, 1 B/sample out")
+        spec["compact_kernel"] = ("hbm", 1 * marched + 20 * kept + 8 * R, "1 B/marched sample + 8 B/kept in, 12 B/kept out")
     out = []
     for k, (ms, launches) in sorted(timeline.items(), key=lambda kv: -kv[1][0]):
         e = {"kernel": k, "ms_per_step": ms, "launches_per_step": launches}
@@ -413,7 +420,7 @@ def main():
         head_step, tail_step = marched_step, 0.0
     n_refresh = sum(1 for i in range(snap["n_iter"], snap["n_iter"] + args.steps) if i % tr.GRID_EVERY == 0)
     cells = tr.acc_grid.num_cells * (2 if tr.vessel_acc_grid is not None else 1) * (1.0 if snap["n_iter"] < 256 else 0.5)
-    counts = dict(rays=R, head=head_step, tail=tail_step, kept=kept_step, pool=pool.n_train_rays if pool.weights is not None else 0,
+    counts = dict(rays=R, head=head_step, tail=tail_step, kept=kept_step, evals=float(sum(tl_n)) / args.steps, pool=pool.n_train_rays if pool.weights is not None else 0,
                   params=MLP_PARAMS.get((w["enc"], w["L"], w["H"]), 0), grid_cells=cells * n_refresh / args.steps)
 
     # ---------------- e2e arm: host buffers in, loss out, every step (same snapshot, median of 3 windows)
@@ -455,7 +462,8 @@ def main():
                 burst = float(peaks.get("bf16_tflops", 1590.0))
                 sust = float(peaks.get("bf16_tflops_sustained", 1400.0))
                 roofline = {"bound": "tensor", "achieved": ach, "peak": burst, "unit": "TFLOP/s", "frac": ach / burst, "traffic": None,
-                            "kernel": "mlp_fwd_tc_kernel<ALPHA> (no-grad visibility pass, steady regime)",
+                            "kernel": ("mlp256_fwd_kernel<ALPHA>" if w["H"] == 256 else "mlp_fwd_tc_kernel<ALPHA> [three-slot mlp_fwd3_tc_kernel]") +
+                                      " (no-grad visibility pass, steady regime)",
                             "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst; the stricter of the two measured peaks)" if peaks
                                             else "fallback 1.59 PFLOP/s"),
                             "frac_of_sustained_peak": ach / sust,

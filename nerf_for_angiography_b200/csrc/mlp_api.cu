@@ -19,6 +19,15 @@ int tc_forward(const MlpLayout& L, const float* params, const void* packed, cons
                void* saved, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 int tc_backward(const MlpLayout& L, const float* params, const void* packed, const angio_samples& in, const void* saved,
                 const float* grad_out, float* grad_params, void* workspace, int64_t workspace_bytes, cudaStream_t st);
+// width 256 (mlp_tc256.cu): weights streamed through shared memory
+bool tc256_supported(const MlpLayout& L);
+int64_t tc256_packed_bytes(const MlpLayout& L);
+int64_t tc256_workspace_bytes(const MlpLayout& L, int64_t n, int training);
+int64_t tc256_saved_bytes(const MlpLayout& L, int64_t n);
+int tc256_pack_weights(const MlpLayout& L, const float* params, void* packed, cudaStream_t st);
+int tc256_forward(const MlpLayout& L, const void* packed, const angio_samples& in, int out_mode, float* out, void* saved, cudaStream_t st);
+int tc256_backward(const MlpLayout& L, const void* packed, const angio_samples& in, const void* saved, const float* grad_out,
+                   float* grad_params, void* workspace, int64_t workspace_bytes, cudaStream_t st);
 }  // namespace angio
 
 using angio::MlpLayout;
@@ -47,6 +56,7 @@ extern "C" int64_t angio_mlp_workspace_bytes(const angio_mlp_desc* desc, int64_t
   if (!angio::make_layout(desc, &L) || n < 0) { angio::set_error("angio_mlp_workspace_bytes: invalid arguments"); return ANGIO_ERR_INVALID_ARG; }
   if (precision == ANGIO_PREC_FP32) return angio::simt_workspace_bytes(L, n, training);
   if (precision == ANGIO_PREC_BF16 && angio::tc_supported(L)) return angio::tc_workspace_bytes(L, n, training);
+  if (precision == ANGIO_PREC_BF16 && angio::tc256_supported(L)) return angio::tc256_workspace_bytes(L, n, training);
   angio::set_error("angio_mlp_workspace_bytes: unsupported precision/shape");
   return ANGIO_ERR_UNSUPPORTED;
 }
@@ -55,18 +65,21 @@ extern "C" int64_t angio_mlp_saved_bytes(const angio_mlp_desc* desc, int64_t n, 
   if (!angio::make_layout(desc, &L) || n < 0) { angio::set_error("angio_mlp_saved_bytes: invalid arguments"); return ANGIO_ERR_INVALID_ARG; }
   if (precision == ANGIO_PREC_FP32) return angio::simt_saved_bytes(L, n);
   if (precision == ANGIO_PREC_BF16 && angio::tc_supported(L)) return angio::tc_saved_bytes(L, n);
+  if (precision == ANGIO_PREC_BF16 && angio::tc256_supported(L)) return angio::tc256_saved_bytes(L, n);
   angio::set_error("angio_mlp_saved_bytes: unsupported precision/shape");
   return ANGIO_ERR_UNSUPPORTED;
 }
 extern "C" int64_t angio_mlp_packed_bytes(const angio_mlp_desc* desc) {
   MlpLayout L;
   if (!angio::make_layout(desc, &L)) { angio::set_error("angio_mlp_packed_bytes: invalid descriptor"); return ANGIO_ERR_INVALID_ARG; }
+  if (angio::tc256_supported(L)) return angio::tc256_packed_bytes(L);
   if (!angio::tc_supported(L)) { angio::set_error("angio_mlp_packed_bytes: shape not supported by the bf16 path"); return ANGIO_ERR_UNSUPPORTED; }
   return angio::tc_packed_bytes(L);
 }
 extern "C" int angio_mlp_pack_weights(const angio_mlp_desc* desc, const float* params, void* packed, void* stream) {
   MlpLayout L;
   ANGIO_REQUIRE(angio::make_layout(desc, &L) && params && packed, "angio_mlp_pack_weights: bad arguments");
+  if (angio::tc256_supported(L)) return angio::tc256_pack_weights(L, params, packed, angio::as_stream(stream));
   if (!angio::tc_supported(L)) { angio::set_error("angio_mlp_pack_weights: shape not supported by the bf16 path"); return ANGIO_ERR_UNSUPPORTED; }
   return angio::tc_pack_weights(L, params, packed, angio::as_stream(stream));
 }
@@ -91,8 +104,9 @@ extern "C" int angio_mlp_forward(const angio_mlp_desc* desc, const float* params
   if (precision == ANGIO_PREC_FP32)
     return angio::simt_forward(L, params, *in, out_mode, out, saved, workspace, workspace_bytes, angio::as_stream(stream));
   if (precision == ANGIO_PREC_BF16) {
-    if (!angio::tc_supported(L)) { angio::set_error("angio_mlp_forward: shape not supported by the bf16 tcgen05 path"); return ANGIO_ERR_UNSUPPORTED; }
     ANGIO_REQUIRE(packed, "angio_mlp_forward: bf16 path needs the packed weight image (angio_mlp_pack_weights)");
+    if (angio::tc256_supported(L)) return angio::tc256_forward(L, packed, *in, out_mode, out, saved, angio::as_stream(stream));
+    if (!angio::tc_supported(L)) { angio::set_error("angio_mlp_forward: shape not supported by the bf16 tcgen05 path"); return ANGIO_ERR_UNSUPPORTED; }
     return angio::tc_forward(L, params, packed, *in, out_mode, out, saved, workspace, workspace_bytes, angio::as_stream(stream));
   }
   angio::set_error("angio_mlp_forward: unknown precision %d", precision);
@@ -112,8 +126,10 @@ extern "C" int angio_mlp_backward(const angio_mlp_desc* desc, const float* param
   if (precision == ANGIO_PREC_FP32)
     return angio::simt_backward(L, params, *in, saved, grad_out, grad_params, workspace, workspace_bytes, angio::as_stream(stream));
   if (precision == ANGIO_PREC_BF16) {
-    if (!angio::tc_supported(L)) { angio::set_error("angio_mlp_backward: shape not supported by the bf16 tcgen05 path"); return ANGIO_ERR_UNSUPPORTED; }
     ANGIO_REQUIRE(packed, "angio_mlp_backward: bf16 path needs the packed weight image");
+    if (angio::tc256_supported(L))
+      return angio::tc256_backward(L, packed, *in, saved, grad_out, grad_params, workspace, workspace_bytes, angio::as_stream(stream));
+    if (!angio::tc_supported(L)) { angio::set_error("angio_mlp_backward: shape not supported by the bf16 tcgen05 path"); return ANGIO_ERR_UNSUPPORTED; }
     return angio::tc_backward(L, params, packed, *in, saved, grad_out, grad_params, workspace, workspace_bytes, angio::as_stream(stream));
   }
   angio::set_error("angio_mlp_backward: unknown precision %d", precision);

@@ -531,22 +531,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
 // 32 packed bf16x2 words of the next layer's A operand straight back into the first half of them (no other warp ever touches
 // them).  A slot then needs ONE 128-column region while it is in its epilogue and a second one only while its MMA runs (the
 // accumulator being written).  The tensor pipe executes MMAs one after the other, so a single spare region is enough:
-// 3 slots + 1 spare = 4 x 128 columns = all of TMEM.  All MMAs are issued by ONE thread in strict rotation
-// (slot 0, 1, 2, 0, ...): MMA number m reads its A operand from region m % 4 and writes its accumulator to region (m + 3) % 4,
-// which is the region MMA m - 1 (previous slot, already issued, executes earlier in the in-order tensor pipe) read its A from.
-// The slot's next stage is MMA m + 3 and reads region (m + 3) % 4: the epilogue's in-place operand.
+// 3 slots + 1 spare = 4 x 128 columns = all of TMEM.  The MMA groups are issued in strict rotation (slot 0, 1, 2, 0, ...):
+// group number m reads its A operand from region m % 4 and writes its accumulator to region (m + 3) % 4, which is the region
+// group m - 1 (previous slot, completely issued before group m starts, and the tensor pipe executes in issue order) read its A
+// from.  The slot's next stage is group m + 3 and reads region (m + 3) % 4: the epilogue's in-place operand.
+// One issuing warp PER SLOT, an issue token passed around after a group's last MMA has been accepted: tcgen05.mma issue blocks
+// while the tensor queue is full, so a single issuing thread leaves the pipe drained between groups (tools/trace_fwd.py: ~330
+// cycles of pipe start-up + ~280 cycles of loop latency per group); with the next slot's issuer already waiting for the token
+// its first MMA queues up behind the current group's last ones.
 //   region layout (128 fp32 columns, lane = sample row):  hidden-layer A operand: K-steps 0..3 (hidden 0..63) in columns [0, 32),
 //   K-steps 4..7 (hidden 64..127) in columns [64, 96) -- each column half is written by the warp that owns it;
 //   first-layer features: 16-column chunk c (K-step c) in columns (c & 1) * 64 + (c >> 1) * 8.
-// Threads: warp 0 = weight load + the MMA issuer, warps 1..24 = three tile groups of 8 warps (4 TMEM lane quadrants x 2 column
-// halves).  25 warps leave 80 registers per thread, so an epilogue handles its 64 columns in two passes of 32.
+// Threads: warps 0..2 = MMA issuers of slots 0..2 (warp 0 also loads the weights), warps 3..26 = three tile groups of 8 warps
+// (4 TMEM lane quadrants x 2 column halves).  27 warps leave 72 registers per thread (7 warps on an SM sub-partition), so an
+// epilogue handles its 64 columns in two passes of 32.
 constexpr int kSlots3 = 3;
-constexpr int kThreads3 = 32 + kSlots3 * kGroupThreads;   // 800
+constexpr int kThreads3 = kSlots3 * 32 + kSlots3 * kGroupThreads;   // 864
 
 struct __align__(8) PipeBarriers3 {
   uint64_t w_ready;
   uint64_t a_ready[kSlots3];
   uint64_t acc_ready[kSlots3];
+  uint64_t turn[kSlots3];     // issue token: slot s may issue its next MMA group once turn[s] has flipped
   uint32_t tmem_base;
 };
 
@@ -572,7 +578,7 @@ __device__ __forceinline__ float bias_relu_32(const uint32_t (&r)[32], const flo
   return dot0;
 }
 
-template <int OUT_MODE>
+template <int OUT_MODE, bool TRACE>
 __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
                                                                    float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
   const int rounds = (my_tiles + kSlots3 - 1) / kSlots3;
   if (threadIdx.x == 0) {
     mbar_init(&bars.w_ready, 1);
-    for (int s = 0; s < kSlots3; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); }
+    for (int s = 0; s < kSlots3; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); mbar_init(&bars.turn[s], 1); }
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&bars.tmem_base, kTmemCols); tmem_relinquish(); }
@@ -600,47 +606,51 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
   const float* consts = reinterpret_cast<const float*>(smem + P.off_const);
   const int n_stages = P.n_hidden + 1;                 // L+1 layers with N = 128; the 128 -> 1 output layer is a dot product in the last epilogue
 
-  if (warp == 0) {
-    // ===================== weight load + the one MMA issuer =====================
-    if (lane == 0) load_weight_image(smem, packed, P.total_bytes, &bars.w_ready);
+  if (warp < kSlots3) {
+    // ===================== MMA issuer of slot `warp` (warp 0 also loads the weight image) =====================
+    const int s = warp;
+    if (warp == 0 && lane == 0) load_weight_image(smem, packed, P.total_bytes, &bars.w_ready);
     mbar_wait(&bars.w_ready, 0);
     const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 0);
     const uint32_t smem_base = smem_u32(smem);
     const int k0_steps = P.k0_pad / 16;
-    uint32_t m = 0;                                    // MMA sequence number: A from region m % 4, D into region (m + 3) % 4
-    uint32_t phase = 0;                                // all slots flip together: one full rotation per (round, stage)
+    uint32_t m = (uint32_t)s;                          // MMA group number: A from region m % 4, D into region (m + 3) % 4
+    uint32_t phase = 0, it = 0;
     for (int rd = 0; rd < rounds; ++rd) {
-      for (int st = 0; st < n_stages; ++st) {
+      for (int st = 0; st < n_stages; ++st, m += kSlots3, ++it) {
         const uint32_t wbase = smem_base + w_offset(st);
-#pragma unroll
-        for (int s = 0; s < kSlots3; ++s, ++m) {
-          mbar_wait(&bars.a_ready[s], phase);
-          fence_after_sync();
-          if (lane == 0) {
-            trace_event3(0, s, st, rd);
-            const uint32_t a_reg = (m & 3u) * 128u, d_reg = ((m + 3u) & 3u) * 128u;
-            if (st == 0) {
-              for (int k = 0; k < k0_steps; ++k)
-                mma_ts(d_reg, a_reg + (k & 1) * 64 + (k >> 1) * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, k > 0);
-            } else {
-#pragma unroll
-              for (int k = 0; k < kH / 16; ++k)
-                mma_ts(d_reg, a_reg + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc,
-                       k > 0);
-            }
-            mma_commit(&bars.acc_ready[s]);
-            trace_event3(1, s, st, rd);
-          }
-          __syncwarp();
-        }
+        mbar_wait(&bars.a_ready[s], phase);
         phase ^= 1;
+        // the token: slot 0 owns it at the start, afterwards turn[s] flips once per rotation
+        if (s == 0) { if (it > 0) mbar_wait(&bars.turn[0], (it - 1) & 1); }
+        else mbar_wait(&bars.turn[s], it & 1);
+        fence_after_sync();
+        if (lane == 0) {
+          if (TRACE) trace_event3(0, s, st, rd);
+          const uint32_t a_reg = (m & 3u) * 128u, d_reg = ((m + 3u) & 3u) * 128u;
+          if (st == 0) {
+            for (int k = 0; k < k0_steps; ++k)
+              mma_ts(d_reg, a_reg + (k & 1) * 64 + (k >> 1) * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, k > 0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < kH / 16; ++k)
+              mma_ts(d_reg, a_reg + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc,
+                     k > 0);
+          }
+          // the whole group has been accepted by the tensor queue: the next slot may issue (strictly behind this group -- its
+          // accumulator region is the one this group reads its A operand from)
+          mbar_arrive(&bars.turn[(s + 1) % kSlots3]);
+          mma_commit(&bars.acc_ready[s]);
+          if (TRACE) trace_event3(1, s, st, rd);
+        }
+        __syncwarp();
       }
     }
   } else {
     // ===================== tile groups: features, epilogues, output =====================
-    const int g = (warp - 1) / 8;                 // slot
+    const int g = (warp - kSlots3) / 8;           // slot
     const int q = warp % 4;                       // TMEM lane quadrant (hardware rule: warp w accesses lanes 32 * (w % 4) ..)
-    const int h = ((warp - 1) % 8) / 4;           // column half
+    const int h = ((warp - kSlots3) % 8) / 4;     // column half
     const int row = q * 32 + lane;                // sample row inside the tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     mbar_wait(&bars.w_ready, 0);                  // biases / coefficients live in the packed image
@@ -694,7 +704,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
-        if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(2, g, l, rd);
+        if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(2, g, l, rd);
         const float* bias = consts + l * 128 + h * 64;
         uint32_t r[32], pk[16];
         tmem_ld32(reg, r);
@@ -706,7 +716,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         bias_relu_32<false>(r, bias + 32, nullptr, pk);
         tmem_st16(reg + 16, pk);
         signal_a_ready(&bars.a_ready[g], lane);
-        if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(3, g, l, rd);
+        if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(3, g, l, rd);
       }
       // ---- last hidden layer + output layer: logit = w_out . relu(z_{L+1}) + b_out on the CUDA cores, in fp32
       {
@@ -716,7 +726,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
-        if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(2, g, l, rd);
+        if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(2, g, l, rd);
         const float* bias = consts + l * 128 + h * 64;
         uint32_t r[32], pk[16];
         tmem_ld32(reg, r);
@@ -729,7 +739,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         if (more) {
           store_features(((m + 3u) & 3u) * 128u, f0, f1);
           signal_a_ready(&bars.a_ready[g], lane);
-          if (lane == 0 && (warp - 1) % 8 == 0) trace_event3(3, g, l, rd);
+          if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(3, g, l, rd);
         }
         dot += bias_relu_32<true>(r, bias + 32, w_out + 32, pk);
         // the h = 1 warp hands its half of the dot product to the h = 0 warp of the same row quadrant
@@ -1186,13 +1196,16 @@ template <int MODE>
 static int launch_fwd3(const TcPlan& P, const void* packed, const angio_samples& in, float* out, cudaStream_t st) {
   const size_t smem = (size_t)P.total_bytes + 1024;
   static size_t cached = 0;
-  if (int rc = ensure_smem(mlp_fwd3_tc_kernel<MODE>, smem, &cached)) return rc;
+  const bool trace = getenv("ANGIO_TRACE") != nullptr;      // tools/trace_fwd.py: the instantiation with clock stamps
+  static size_t cached_t = 0;
+  if (int rc = trace ? ensure_smem(mlp_fwd3_tc_kernel<MODE, true>, smem, &cached_t) : ensure_smem(mlp_fwd3_tc_kernel<MODE, false>, smem, &cached)) return rc;
   if (in.n >= ((int64_t)1 << 31) - (int64_t)kTile * 1024) { set_error("mlp_fwd3_tc_kernel: at most 2^31 samples per launch"); return ANGIO_ERR_INVALID_ARG; }
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
   int grid = sm_count();
   if (n_tiles < grid) grid = (int)n_tiles;
   angio::note_launch(MODE == ANGIO_OUT_ALPHA ? "mlp_fwd_tc_kernel<ALPHA>" : MODE == ANGIO_OUT_SIGMA ? "mlp_fwd_tc_kernel<SIGMA>" : "mlp_fwd_tc_kernel<LOGIT>");
-  mlp_fwd3_tc_kernel<MODE><<<grid, kThreads3, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
+  if (trace) mlp_fwd3_tc_kernel<MODE, true><<<grid, kThreads3, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
+  else mlp_fwd3_tc_kernel<MODE, false><<<grid, kThreads3, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
   return finish_launch("mlp_fwd3_tc_kernel");
 }
 

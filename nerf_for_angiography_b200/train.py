@@ -97,6 +97,7 @@ class Trainer:
         # draw + march the next batch under the gradient all-reduce (sync-free mode); ANGIO_PREFETCH=0 keeps the plain order
         self.prefetch = os.environ.get("ANGIO_PREFETCH", "1") != "0"
         self.shard_grid = os.environ.get("ANGIO_SHARD_GRID", "1") != "0"
+        self.train_memory_bytes = int(os.environ.get("ANGIO_TRAIN_MEMORY_GB", "0")) * 2 ** 30 or int(0.4 * torch.cuda.mem_get_info(self.dev)[0])
         self._prefetched = None
         self._march_calls = 0
         # visibility pass with early ray termination (bf16 path): number of leading samples per ray evaluated before the rays
@@ -295,10 +296,29 @@ class Trainer:
                 kw = dict(rays_o=o, rays_d=d, ray_idx=ray_idx, t_starts=t0, t_ends=t1)
                 if sync_free:
                     kw["n_dev"] = offsets[R:R + 1]
-                logits, saved = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
-                pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
-                                                                 pool=self.pool_bufs if sync_free else None)
-                ops.mlp_backward(m._desc, self.kflat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
+                chunk = None if sync_free else self._backward_chunk(n_kept)
+                if chunk is None:
+                    logits, saved = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kw)
+                    pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world,
+                                                                     pool=self.pool_bufs if sync_free else None)
+                    ops.mlp_backward(m._desc, self.kflat, self.packed, saved, glogits, prec, grad_params=self.grad, pool=self.pool_bufs, **kw)
+                else:
+                    # The saved tile images of ALL kept samples would not fit (8 x 256: 9.4 KB per sample): logits of every sample
+                    # first (no activations kept), composite + loss, then forward(train) -> dgrad -> wgrad chunk by chunk with
+                    # the parameter gradient accumulated over the chunks.  Same numbers as the one-shot path up to the fp32
+                    # summation order of the weight gradients.
+                    logits = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, **kw)
+                    pix, glogits, loss_sum = ops.composite_mse_fused(logits, t0, t1, offsets, target, R * self.world)
+                    self.grad.zero_()
+                    if self._grad_chunk is None:
+                        self._grad_chunk = torch.empty_like(self.grad)
+                    for a in range(0, n_kept, chunk):
+                        b = min(n_kept, a + chunk)
+                        kc = dict(rays_o=o, rays_d=d, ray_idx=ray_idx[a:b], t_starts=t0[a:b], t_ends=t1[a:b])
+                        _, saved = ops.mlp_forward(m._desc, self.kflat, self.packed, ops.OUT_LOGIT, prec, saved=True, pool=self.pool_bufs, **kc)
+                        ops.mlp_backward(m._desc, self.kflat, self.packed, saved, glogits[a:b], prec, grad_params=self._grad_chunk,
+                                         pool=self.pool_bufs, **kc)
+                        self.grad[:-1].add_(self._grad_chunk[:-1])
                 m._map_grad_(self.grad)                                     # BARF: chain rule through the folded mask (no-op otherwise)
                 loss = loss_sum / R
             else:
@@ -342,6 +362,22 @@ class Trainer:
         return self.last
 
     n_iter_adam = 0
+    _grad_chunk = None
+
+    def _backward_chunk(self, n_kept):
+        """Samples per forward(train)/backward chunk on the one-sync path, or None when the saved tile images + backward
+        workspace of all n_kept samples fit in `train_memory_bytes` (default: 40 % of the HBM that was free at construction)."""
+        if self._bytes_per_sample is None:
+            lib, desc, prec = _lib.load(), self.model._desc, self.model._precision_id
+            probe = 1 << 20
+            self._bytes_per_sample = (int(lib.angio_mlp_saved_bytes(ctypes.byref(desc), probe, prec)) +
+                                      int(lib.angio_mlp_workspace_bytes(ctypes.byref(desc), probe, prec, 1))) / probe
+        if n_kept * self._bytes_per_sample * 2.1 <= self.train_memory_bytes:      # the buffer pool doubles when it grows
+            return None
+        chunk = int(self.train_memory_bytes / (2.1 * self._bytes_per_sample)) // 128 * 128
+        return max(chunk, 128 * 148)
+
+    _bytes_per_sample = None
 
     def _check_sampler_status(self, totals):
         """The on-device ray sampler reports a failed draw (candidate buffer overflow / under-fill; its ids are then all ray 0)

@@ -1,6 +1,7 @@
 """Pipeline trace of the three-slot inference forward (CTA 0): per-stage hand-off / MMA issue / epilogue latencies in SM cycles.
     python tools/trace_fwd.py            # prints the event list of rounds 2..3 and a per-phase summary"""
 import ctypes, os, sys
+os.environ["ANGIO_TRACE"] = "1"
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import bench, nerf_for_angiography_b200 as A
