@@ -406,9 +406,14 @@ def main():
 
     # ---------------- per-kernel timeline of the same window (CUDA events at every launch; a separate, untimed pass)
     tr.restore(snap)
+    kernel_timeline(lib, lambda: tr.step(), 1)          # untimed: creates the library's event pool outside the measured pass
+    tr.restore(snap)
     sync_all()
     tl_totals, tr.kernel_events = [], []
+    gc.collect()
+    gc.disable()                                        # a collector pause would drain the stream and be billed to one kernel
     timeline = kernel_timeline(lib, lambda: [tl_totals.append(tr.step()["totals"]) for _ in range(args.steps)], args.steps)
+    gc.enable()
     tl_host = [t.tolist() for t in tl_totals]
     tl_n = [int(c.item()) if isinstance(c, torch.Tensor) else int(c) for _, _, c in tr.kernel_events]
     tr.kernel_events = None
@@ -509,6 +514,9 @@ def main():
                                  "samples_kept_per_step": float(cnt[3]) / world / args.steps,
                                  "what": "random-init network: opaque field, every ray terminates inside its first 32 samples"},
                 "mlp_evals_visibility_per_step": float(sum(kernel_n)) / max(args.steps, 1),
+                "visibility_launches": ({"head_samples_per_launch": float(np.mean(kernel_n[0::2])), "tail_samples_per_launch": float(np.mean(kernel_n[1::2])),
+                                         "head_ms": float(np.mean(kernel_ms[0::2])), "tail_ms": float(np.mean(kernel_ms[1::2]))}
+                                        if tr.lazy_march and len(kernel_n) == 2 * args.steps else None),
                 "samples_marched_per_step": float(cnt[0]) / world / args.steps, "samples_kept_per_step": float(cnt[1]) / world / args.steps,
                 "samples_per_s_marched": float(cnt[0]) / (ms * 1e-3), "samples_per_s_kept": float(cnt[1]) / (ms * 1e-3),
                 "clocks": clk, "gpu_launches": launches,

@@ -52,6 +52,55 @@ __global__ void __launch_bounds__(256) visibility_mask_kernel(const float* __res
   }
 }
 
+// Thread-per-ray variant for LONG segments (the tail of lazily marched rays in the steady training regime: ~270 samples per ray,
+// nothing terminates early).  The transmittance chain is serial per ray either way; walking it with warp shuffles costs 32
+// dependent shuffle + multiply steps per 32 samples (190 us for 17 M samples, latency-bound), whereas one thread per ray runs the
+// same chain as plain register arithmetic with its alphas prefetched eight at a time -- the 32 lanes of a warp stream 32
+// different segments, each lane consuming its own 128-byte lines out of L1.  Same arithmetic, same order: bit-identical flags.
+__global__ void __launch_bounds__(128) visibility_mask_ray_kernel(const float* __restrict__ alphas, const int32_t* __restrict__ offsets,
+                                                                  int64_t n_rays, float eps, float thre, uint8_t* __restrict__ keep,
+                                                                  int32_t* __restrict__ kept_counts, const float* __restrict__ t_init,
+                                                                  const int32_t* __restrict__ base_counts, const float* __restrict__ thre_cap) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= n_rays) return;
+  if (thre_cap) thre = fminf(thre, *thre_cap);
+  const int beg = offsets[r], end = offsets[r + 1];
+  float T = t_init ? t_init[r] : 1.0f;
+  int kept = 0;
+  int i = beg;
+  bool dead = false;
+  auto one = [&](float a) -> uint32_t {          // the serial step: flag of this sample, then T *= (1 - alpha)
+    bool vis = T >= eps;
+    if (thre > 0.0f) vis = vis && (a >= thre);
+    kept += vis ? 1 : 0;
+    T = __fmul_rn(T, __fsub_rn(1.0f, a));
+    return vis ? 1u : 0u;
+  };
+  // scalar head up to a 16-byte boundary of the alpha array, then 16 samples per round as four float4 loads (a lane's loads and
+  // its 4-byte flag stores stay inside its own cache lines: a quarter of the memory transactions of scalar accesses)
+  for (; i < end && (i & 3) != 0; ++i) keep[i] = (uint8_t)one(alphas[i]);
+  dead = T < eps;
+  while (i + 16 <= end && !dead) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(alphas + i + 4 * k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t f = one(v[k].x);
+      f |= one(v[k].y) << 8;
+      f |= one(v[k].z) << 16;
+      f |= one(v[k].w) << 24;
+      *reinterpret_cast<uint32_t*>(keep + i + 4 * k) = f;
+    }
+    i += 16;
+    // alpha in [0, 1] makes T non-increasing: nothing behind this point can be visible
+    dead = T < eps;
+  }
+  for (; i < end && !dead; ++i) { keep[i] = (uint8_t)one(alphas[i]); dead = T < eps; }
+  for (; i < end; ++i) keep[i] = 0;
+  kept_counts[r] = kept + (base_counts ? base_counts[r] : 0);
+}
+
 __global__ void __launch_bounds__(256) compact_kernel(const uint8_t* __restrict__ keep, const int32_t* __restrict__ offsets,
                                                       const int32_t* __restrict__ new_offsets, int64_t n_rays,
                                                       const float* __restrict__ t_starts, const float* __restrict__ t_ends,
@@ -220,6 +269,14 @@ extern "C" int angio_visibility_mask(const float* alphas, const int32_t* offsets
                                      const int32_t* base_counts, const float* alpha_thre_cap, void* stream) {
   ANGIO_REQUIRE(offsets && kept_counts && n_rays >= 0, "angio_visibility_mask: bad arguments");
   if (n_rays == 0) return 0;
+  // Long segments (a resumed march: t_init given): one thread per ray; otherwise the warp-per-ray kernel, whose chunked early
+  // exit never reads alphas behind the first chunk that terminates a ray (the two-phase pass leaves those undefined).
+  if (t_init != nullptr && (reinterpret_cast<uintptr_t>(alphas) & 15) == 0 && (reinterpret_cast<uintptr_t>(keep) & 3) == 0) {
+    angio::note_launch("visibility_mask_ray_kernel");
+    visibility_mask_ray_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps, alpha_thre,
+                                                                                                   keep, kept_counts, t_init, base_counts, alpha_thre_cap);
+    return angio::finish_launch("angio_visibility_mask");
+  }
   angio::note_launch("visibility_mask_kernel"); visibility_mask_kernel<<<warp_grid(n_rays), 256, 0, angio::as_stream(stream)>>>(alphas, offsets, n_rays, early_stop_eps,
                                                                                  alpha_thre, keep, kept_counts, t_init, base_counts, alpha_thre_cap);
   return angio::finish_launch("angio_visibility_mask");
