@@ -362,7 +362,8 @@ def main():
     sync_all()
     every = max(1, args.steps // 8)
     window_ms, step_totals, launches = [], [], 0
-    if tr.peer is not None:
+    use_peer = tr.peer is not None and tr.sync_free     # the one-sync loop (config 4) exchanges gradients with NCCL all_reduce
+    if use_peer:
         tr.peer.wait_stats.zero_()
     for rep in range(args.repeats):
         tr.restore(snap)
@@ -394,7 +395,7 @@ def main():
     tr.kernel_events = None
     last_loss = float(body.out["loss"])
     wait = None
-    if tr.peer is not None:
+    if use_peer:
         ws = tr.peer.wait_stats.tolist()
         wt = torch.tensor([ws[0] / max(ws[1], 1) * 1e-3, ws[2] * 1e-3], dtype=torch.float64, device=dev)     # mean / longest wait of this rank, us
         mx, mean = wt.clone(), wt.clone()

@@ -542,17 +542,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_fwd_tc_kernel(const uint8_t* 
 //   region layout (128 fp32 columns, lane = sample row):  hidden-layer A operand: K-steps 0..3 (hidden 0..63) in columns [0, 32),
 //   K-steps 4..7 (hidden 64..127) in columns [64, 96) -- each column half is written by the warp that owns it;
 //   first-layer features: 16-column chunk c (K-step c) in columns (c & 1) * 64 + (c >> 1) * 8.
-// Threads: warps 0..2 = MMA issuers of slots 0..2 (warp 0 also loads the weights), warps 3..26 = three tile groups of 8 warps
-// (4 TMEM lane quadrants x 2 column halves).  27 warps leave 72 registers per thread (7 warps on an SM sub-partition), so an
-// epilogue handles its 64 columns in two passes of 32.
+// Threads: warps 0..2 = MMA issuers of slots 0..2 (warp 0 also loads the weights), warp 3 = input loader, warps 4..27 = three
+// tile groups of 8 warps (4 TMEM lane quadrants x 2 column halves).  28 warps leave 72 registers per thread (7 warps on an SM
+// sub-partition), so an epilogue handles its 64 columns in two passes of 32.
+// The loader warp fetches the inputs of every slot's next tile (sample id -> ray id / interval -> origin / direction: two or
+// three DEPENDENT global loads, ~1 000 cycles when a thread issues them back to back), forms the sample positions and leaves
+// (x, dt, output index) in a double-buffered shared-memory block per slot, so the epilogue warps never wait on global memory:
+// in the trace the first-layer rotation of a tile took 2 266 cycles for 9 MMAs because every epilogue warp sat in that chain.
 constexpr int kSlots3 = 3;
-constexpr int kThreads3 = kSlots3 * 32 + kSlots3 * kGroupThreads;   // 864
+constexpr int kEpiWarp0 = kSlots3 + 1;                                  // first epilogue warp
+constexpr int kThreads3 = kEpiWarp0 * 32 + kSlots3 * kGroupThreads;     // 896
+
+struct InBuf3 {               // inputs of one 128-sample tile, written by the loader warp
+  float x[3][kTile];
+  float dt[kTile];
+  int idx[kTile];             // where the row's output goes; -1 = no sample in this row
+};
 
 struct __align__(8) PipeBarriers3 {
   uint64_t w_ready;
   uint64_t a_ready[kSlots3];
   uint64_t acc_ready[kSlots3];
   uint64_t turn[kSlots3];     // issue token: slot s may issue its next MMA group once turn[s] has flipped
+  uint64_t in_ready[kSlots3][2];   // loader -> tile group: input block filled
+  uint64_t in_free[kSlots3][2];    // tile group (8 warps) -> loader: input block consumed
   uint32_t tmem_base;
 };
 
@@ -584,6 +597,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ PipeBarriers3 bars;
   __shared__ float s_dot[kSlots3][kTile];                                  // output layer: column-half 1's partial dot products
+  __shared__ InBuf3 s_in[kSlots3][2];
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / 32), 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x % 32;
   int n = (int)in.n;                                                       // < 2^31 (checked by the launcher): 32-bit indices save registers
@@ -595,7 +609,10 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
   const int rounds = (my_tiles + kSlots3 - 1) / kSlots3;
   if (threadIdx.x == 0) {
     mbar_init(&bars.w_ready, 1);
-    for (int s = 0; s < kSlots3; ++s) { mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); mbar_init(&bars.turn[s], 1); }
+    for (int s = 0; s < kSlots3; ++s) {
+      mbar_init(&bars.a_ready[s], kGroupThreads / 32); mbar_init(&bars.acc_ready[s], 1); mbar_init(&bars.turn[s], 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(&bars.in_ready[s][b], 1); mbar_init(&bars.in_free[s][b], kGroupThreads / 32); }
+    }
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(&bars.tmem_base, kTmemCols); tmem_relinquish(); }
@@ -646,11 +663,67 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         __syncwarp();
       }
     }
+  } else if (warp == kSlots3) {
+    // ===================== input loader: tile (round rd, slot s) -> s_in[s][rd & 1], two tiles ahead of the tile groups =====================
+    // (a CTA without tiles -- the device-resident sample count can be far below the capacity the grid was sized for -- still
+    // hands every tile group one empty block: the groups take their first inputs unconditionally)
+    for (int rd = 0; rd < (rounds > 0 ? rounds : 1); ++rd) {
+      const int b = rd & 1;
+      for (int s = 0; s < kSlots3; ++s) {
+        mbar_wait(&bars.in_free[s][b], (uint32_t)(((rd >> 1) & 1) ^ 1));      // first use of each block passes immediately
+        const int jt = rd * kSlots3 + s;
+        const int base = ((int)blockIdx.x + jt * (int)gridDim.x) * kTile;
+        InBuf3& B = s_in[s][b];
+        int ii[4], rr[4];
+        float ts[4], te[4];
+        bool vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                  // rows lane, lane + 32, lane + 64, lane + 96: all loads of a level in flight together
+          ii[k] = base + lane + 32 * k;
+          vv[k] = (jt < my_tiles) && (ii[k] < n);
+          if (vv[k] && in.sample_idx) ii[k] = in.sample_idx[ii[k]];
+        }
+        if (in.points) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+            if (vv[k]) { x0 = in.points[(int64_t)ii[k] * 3]; x1 = in.points[(int64_t)ii[k] * 3 + 1]; x2 = in.points[(int64_t)ii[k] * 3 + 2]; }
+            const int r = lane + 32 * k;
+            B.x[0][r] = x0; B.x[1][r] = x1; B.x[2][r] = x2; B.dt[r] = 0.f; B.idx[r] = vv[k] ? ii[k] : -1;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            rr[k] = 0; ts[k] = 0.f; te[k] = 0.f;
+            if (vv[k]) { rr[k] = in.ray_idx[ii[k]]; ts[k] = in.t_starts[ii[k]]; te[k] = in.t_ends[ii[k]]; }
+          }
+          float o[4][3], d[4][3];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              o[k][c] = vv[k] ? in.rays_o[(int64_t)rr[k] * 3 + c] : 0.f;
+              d[k][c] = vv[k] ? in.rays_d[(int64_t)rr[k] * 3 + c] : 0.f;
+            }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int r = lane + 32 * k;
+            const float tsum = __fadd_rn(ts[k], te[k]);            // midpoint, reference operation order (angio::sample_position)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) B.x[c][r] = vv[k] ? __fadd_rn(o[k][c], __fmul_rn(__fmul_rn(d[k][c], tsum), 0.5f)) : 0.f;
+            B.dt[r] = vv[k] ? te[k] - ts[k] : 0.f;
+            B.idx[r] = vv[k] ? ii[k] : -1;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars.in_ready[s][b]);
+      }
+    }
   } else {
     // ===================== tile groups: features, epilogues, output =====================
-    const int g = (warp - kSlots3) / 8;           // slot
+    const int g = (warp - kEpiWarp0) / 8;         // slot
     const int q = warp % 4;                       // TMEM lane quadrant (hardware rule: warp w accesses lanes 32 * (w % 4) ..)
-    const int h = ((warp - kSlots3) % 8) / 4;     // column half
+    const int h = ((warp - kEpiWarp0) % 8) / 4;   // column half
     const int row = q * 32 + lane;                // sample row inside the tile
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     mbar_wait(&bars.w_ready, 0);                  // biases / coefficients live in the packed image
@@ -660,17 +733,16 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     const int pair_bar = 1 + g * 4 + q;           // named barrier shared by the two column-half warps of this row quadrant
     const int nb = 3 * P.basis;
     uint32_t phase = 0;
-    auto fetch = [&](int jt, float (&xx)[3], float& dtt, bool& vv, int& idx) {
-      int ii = ((int)blockIdx.x + jt * (int)gridDim.x) * kTile + row;
-      vv = (jt < my_tiles) && (ii < n);
-      xx[0] = xx[1] = xx[2] = 0.f;
-      dtt = 0.f;
-      if (vv) {
-        if (in.sample_idx) ii = in.sample_idx[ii];      // index list: a subset of the sample arrays (two-phase visibility pass)
-        angio::sample_position(in, ii, xx);
-        if (OUT_MODE == ANGIO_OUT_ALPHA) dtt = in.t_ends[ii] - in.t_starts[ii];
-      }
-      idx = ii;
+    // inputs of tile (round rd) of this slot from the loader's block; the block is handed back as soon as the row is in registers
+    auto take_inputs = [&](int rd, float (&xx)[3], float& dtt, int& idx) {
+      const int b = rd & 1;
+      mbar_wait(&bars.in_ready[g][b], (uint32_t)((rd >> 1) & 1));
+      const InBuf3& B = s_in[g][b];
+      xx[0] = B.x[0][row]; xx[1] = B.x[1][row]; xx[2] = B.x[2][row];
+      dtt = B.dt[row];
+      idx = B.idx[row];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars.in_free[g][b]);
     };
     // this warp's share of the first-layer features: half 0 encodes chunks 0 and 2, half 1 chunk 1 (and 3 when K0 > 48)
     auto encode = [&](const float (&xx)[3], uint32_t (&f0)[8], uint32_t (&f1)[8]) {
@@ -683,20 +755,16 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
       if ((2 + h) * 16 < P.k0_pad) tmem_st8(base + 8, f1);
     };
     float xn[3], dtn;
-    bool vn;
     int in_;
     uint32_t f0[8], f1[8];
-    fetch(g, xn, dtn, vn, in_);
+    take_inputs(0, xn, dtn, in_);
     encode(xn, f0, f1);
     store_features((uint32_t)g * 128u, f0, f1);           // MMA number g reads region g
     signal_a_ready(&bars.a_ready[g], lane);
     for (int rd = 0; rd < rounds; ++rd) {
-      const int j = rd * kSlots3 + g;
-      const int i = in_;                          // where this row's output goes
-      const bool valid = vn;
+      const int i = in_;                          // where this row's output goes (-1: no sample in this row)
       const float dt = dtn;
       const bool more = rd + 1 < rounds;
-      if (more) fetch(j + kSlots3, xn, dtn, vn, in_);   // in flight during this tile's layers
       uint32_t m = (uint32_t)(rd * n_stages) * kSlots3 + g;    // MMA number of this tile's stage 0 (mod 2^32 keeps m % 4)
       // ---- hidden layers: acc + bias -> relu -> bf16 -> in-place A operand of the next layer (this warp: columns [64h, 64h+64))
       for (int l = 0; l < P.n_hidden; ++l, m += kSlots3) {
@@ -704,7 +772,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
-        if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(2, g, l, rd);
+        if (TRACE && lane == 0 && (warp - kEpiWarp0) % 8 == 0) trace_event3(2, g, l, rd);
         const float* bias = consts + l * 128 + h * 64;
         uint32_t r[32], pk[16];
         tmem_ld32(reg, r);
@@ -716,17 +784,20 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         bias_relu_32<false>(r, bias + 32, nullptr, pk);
         tmem_st16(reg + 16, pk);
         signal_a_ready(&bars.a_ready[g], lane);
-        if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(3, g, l, rd);
+        if (TRACE && lane == 0 && (warp - kEpiWarp0) % 8 == 0) trace_event3(3, g, l, rd);
       }
       // ---- last hidden layer + output layer: logit = w_out . relu(z_{L+1}) + b_out on the CUDA cores, in fp32
       {
         const int l = P.n_hidden;
         const uint32_t reg = ((m + 3u) & 3u) * 128u + lane_off + h * 64;
-        if (more) encode(xn, f0, f1);              // next tile's features, computed while the tensor core runs this tile's last layer
+        if (more) {                                // next tile's features, computed while the tensor core runs this tile's last layer
+          take_inputs(rd + 1, xn, dtn, in_);
+          encode(xn, f0, f1);
+        }
         mbar_wait(&bars.acc_ready[g], phase);
         phase ^= 1;
         fence_after_sync();
-        if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(2, g, l, rd);
+        if (TRACE && lane == 0 && (warp - kEpiWarp0) % 8 == 0) trace_event3(2, g, l, rd);
         const float* bias = consts + l * 128 + h * 64;
         uint32_t r[32], pk[16];
         tmem_ld32(reg, r);
@@ -739,7 +810,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         if (more) {
           store_features(((m + 3u) & 3u) * 128u, f0, f1);
           signal_a_ready(&bars.a_ready[g], lane);
-          if (TRACE && lane == 0 && (warp - kSlots3) % 8 == 0) trace_event3(3, g, l, rd);
+          if (TRACE && lane == 0 && (warp - kEpiWarp0) % 8 == 0) trace_event3(3, g, l, rd);
         }
         dot += bias_relu_32<true>(r, bias + 32, w_out + 32, pk);
         // the h = 1 warp hands its half of the dot product to the h = 0 warp of the same row quadrant
@@ -748,7 +819,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
           asm volatile("bar.arrive %0, 64;" ::"r"(pair_bar) : "memory");
         } else {
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-          if (valid && j < my_tiles) out[i] = out_transform<OUT_MODE>(dot + s_dot[g][row] + b_out, dt);
+          if (i >= 0) out[i] = out_transform<OUT_MODE>(dot + s_dot[g][row] + b_out, dt);
         }
       }
     }
