@@ -591,7 +591,7 @@ __device__ __forceinline__ float bias_relu_32(const uint32_t (&r)[32], const flo
   return dot0;
 }
 
-template <int OUT_MODE, bool TRACE>
+template <int OUT_MODE, bool TRACE, bool STAGGER>
 __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t* __restrict__ packed, TcPlan P, angio_samples in,
                                                                    float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -631,37 +631,45 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 0);
     const uint32_t smem_base = smem_u32(smem);
     const int k0_steps = P.k0_pad / 16;
+    // STAGGER (experiment, ANGIO_FWD_STAGGER=1): slot s runs `lead` throw-away first-layer groups before its first tile and the
+    // slots that finish first append such groups at the end, so the three slots work on different layers of their tiles while
+    // every slot still issues a group on every turn (the region rotation depends on that).
+    const int lead = STAGGER ? (s * n_stages) / kSlots3 : 0;
+    const int extra = STAGGER ? ((kSlots3 - 1) * n_stages) / kSlots3 : 0;
+    const int real_turns = rounds * n_stages;
     uint32_t m = (uint32_t)s;                          // MMA group number: A from region m % 4, D into region (m + 3) % 4
-    uint32_t phase = 0, it = 0;
-    for (int rd = 0; rd < rounds; ++rd) {
-      for (int st = 0; st < n_stages; ++st, m += kSlots3, ++it) {
-        const uint32_t wbase = smem_base + w_offset(st);
-        mbar_wait(&bars.a_ready[s], phase);
-        phase ^= 1;
-        // the token: slot 0 owns it at the start, afterwards turn[s] flips once per rotation
-        if (s == 0) { if (it > 0) mbar_wait(&bars.turn[0], (it - 1) & 1); }
-        else mbar_wait(&bars.turn[s], it & 1);
-        fence_after_sync();
-        if (lane == 0) {
-          if (TRACE) trace_event3(0, s, st, rd);
-          const uint32_t a_reg = (m & 3u) * 128u, d_reg = ((m + 3u) & 3u) * 128u;
-          if (st == 0) {
-            for (int k = 0; k < k0_steps; ++k)
-              mma_ts(d_reg, a_reg + (k & 1) * 64 + (k >> 1) * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, k > 0);
-          } else {
+    uint32_t phase = 0;
+    int st = 0, rd = 0;
+    for (int turn = 0; turn < real_turns + extra; ++turn, m += kSlots3) {
+      const bool real = turn >= lead && turn < lead + real_turns;
+      const int stage = real ? st : 0;
+      const uint32_t wbase = smem_base + w_offset(stage);
+      mbar_wait(&bars.a_ready[s], phase);
+      phase ^= 1;
+      // the token: slot 0 owns it at the start, afterwards turn[s] flips once per rotation
+      if (s == 0) { if (turn > 0) mbar_wait(&bars.turn[0], (uint32_t)(turn - 1) & 1u); }
+      else mbar_wait(&bars.turn[s], (uint32_t)turn & 1u);
+      fence_after_sync();
+      if (lane == 0) {
+        if (TRACE && real) trace_event3(0, s, st, rd);
+        const uint32_t a_reg = (m & 3u) * 128u, d_reg = ((m + 3u) & 3u) * 128u;
+        if (stage == 0) {
+          for (int k = 0; k < k0_steps; ++k)
+            mma_ts(d_reg, a_reg + (k & 1) * 64 + (k >> 1) * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, k > 0);
+        } else {
 #pragma unroll
-            for (int k = 0; k < kH / 16; ++k)
-              mma_ts(d_reg, a_reg + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc,
-                     k > 0);
-          }
-          // the whole group has been accepted by the tensor queue: the next slot may issue (strictly behind this group -- its
-          // accumulator region is the one this group reads its A operand from)
-          mbar_arrive(&bars.turn[(s + 1) % kSlots3]);
-          mma_commit(&bars.acc_ready[s]);
-          if (TRACE) trace_event3(1, s, st, rd);
+          for (int k = 0; k < kH / 16; ++k)
+            mma_ts(d_reg, a_reg + (k >> 2) * 64 + (k & 3) * 8, make_smem_desc_sw128(wbase + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024), idesc,
+                   k > 0);
         }
-        __syncwarp();
+        // the whole group has been accepted by the tensor queue: the next slot may issue (strictly behind this group -- its
+        // accumulator region is the one this group reads its A operand from)
+        mbar_arrive(&bars.turn[(s + 1) % kSlots3]);
+        mma_commit(&bars.acc_ready[s]);
+        if (TRACE && real) trace_event3(1, s, st, rd);
       }
+      __syncwarp();
+      if (real && ++st == n_stages) { st = 0; ++rd; }
     }
   } else if (warp == kSlots3) {
     // ===================== input loader: tile (round rd, slot s) -> s_in[s][rd & 1], two tiles ahead of the tile groups =====================
@@ -761,11 +769,20 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     encode(xn, f0, f1);
     store_features((uint32_t)g * 128u, f0, f1);           // MMA number g reads region g
     signal_a_ready(&bars.a_ready[g], lane);
+    const int lead = STAGGER ? (g * n_stages) / kSlots3 : 0;
+    const int trail = STAGGER ? ((kSlots3 - 1) * n_stages) / kSlots3 - lead : 0;
+    for (int rep = 0; rep < lead; ++rep) {                // throw-away first-layer groups: the features follow the slot's region
+      mbar_wait(&bars.acc_ready[g], phase);
+      phase ^= 1;
+      fence_after_sync();
+      store_features((((uint32_t)(rep * kSlots3 + g) + 3u) & 3u) * 128u, f0, f1);
+      signal_a_ready(&bars.a_ready[g], lane);
+    }
     for (int rd = 0; rd < rounds; ++rd) {
       const int i = in_;                          // where this row's output goes (-1: no sample in this row)
       const float dt = dtn;
       const bool more = rd + 1 < rounds;
-      uint32_t m = (uint32_t)(rd * n_stages) * kSlots3 + g;    // MMA number of this tile's stage 0 (mod 2^32 keeps m % 4)
+      uint32_t m = (uint32_t)(rd * n_stages + lead) * kSlots3 + g;    // MMA number of this tile's stage 0 (mod 2^32 keeps m % 4)
       // ---- hidden layers: acc + bias -> relu -> bf16 -> in-place A operand of the next layer (this warp: columns [64h, 64h+64))
       for (int l = 0; l < P.n_hidden; ++l, m += kSlots3) {
         const uint32_t reg = ((m + 3u) & 3u) * 128u + lane_off + h * 64;
@@ -807,8 +824,8 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
         wait_ld();
         // the accumulator is in registers: hand the slot's next tile to the tensor core BEFORE finishing this tile's math.  The
         // features go into the region just drained: it is the A region of this slot's next MMA (number m + 3).
-        if (more) {
-          store_features(((m + 3u) & 3u) * 128u, f0, f1);
+        if (more || trail > 0) {                   // (after the slot's last tile the trailing groups run on stale data)
+          if (more) store_features(((m + 3u) & 3u) * 128u, f0, f1);
           signal_a_ready(&bars.a_ready[g], lane);
           if (TRACE && lane == 0 && (warp - kEpiWarp0) % 8 == 0) trace_event3(3, g, l, rd);
         }
@@ -822,6 +839,12 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
           if (i >= 0) out[i] = out_transform<OUT_MODE>(dot + s_dot[g][row] + b_out, dt);
         }
       }
+    }
+    for (int rep = 0; rep < trail; ++rep) {               // trailing throw-away groups of the slots that started early
+      mbar_wait(&bars.acc_ready[g], phase);
+      phase ^= 1;
+      fence_after_sync();
+      if (rep + 1 < trail) signal_a_ready(&bars.a_ready[g], lane);
     }
   }
   fence_before_sync();
@@ -1266,17 +1289,22 @@ static int ensure_smem(K kernel, size_t smem, size_t* cached) {
 template <int MODE>
 static int launch_fwd3(const TcPlan& P, const void* packed, const angio_samples& in, float* out, cudaStream_t st) {
   const size_t smem = (size_t)P.total_bytes + 1024;
-  static size_t cached = 0;
   const bool trace = getenv("ANGIO_TRACE") != nullptr;      // tools/trace_fwd.py: the instantiation with clock stamps
-  static size_t cached_t = 0;
-  if (int rc = trace ? ensure_smem(mlp_fwd3_tc_kernel<MODE, true>, smem, &cached_t) : ensure_smem(mlp_fwd3_tc_kernel<MODE, false>, smem, &cached)) return rc;
+  const char* sg = getenv("ANGIO_FWD_STAGGER");
+  const bool stagger = sg && sg[0] == '1';                  // experiment: slots on different layers
+  static size_t cached[3] = {0, 0, 0};
+  if (int rc = trace ? ensure_smem(mlp_fwd3_tc_kernel<MODE, true, false>, smem, &cached[0])
+             : stagger ? ensure_smem(mlp_fwd3_tc_kernel<MODE, false, true>, smem, &cached[1])
+                       : ensure_smem(mlp_fwd3_tc_kernel<MODE, false, false>, smem, &cached[2])) return rc;
   if (in.n >= ((int64_t)1 << 31) - (int64_t)kTile * 1024) { set_error("mlp_fwd3_tc_kernel: at most 2^31 samples per launch"); return ANGIO_ERR_INVALID_ARG; }
   const int64_t n_tiles = (in.n + kTile - 1) / kTile;
   int grid = sm_count();
   if (n_tiles < grid) grid = (int)n_tiles;
   angio::note_launch(MODE == ANGIO_OUT_ALPHA ? "mlp_fwd_tc_kernel<ALPHA>" : MODE == ANGIO_OUT_SIGMA ? "mlp_fwd_tc_kernel<SIGMA>" : "mlp_fwd_tc_kernel<LOGIT>");
-  if (trace) mlp_fwd3_tc_kernel<MODE, true><<<grid, kThreads3, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
-  else mlp_fwd3_tc_kernel<MODE, false><<<grid, kThreads3, smem, st>>>(reinterpret_cast<const uint8_t*>(packed), P, in, out);
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(packed);
+  if (trace) mlp_fwd3_tc_kernel<MODE, true, false><<<grid, kThreads3, smem, st>>>(pk, P, in, out);
+  else if (stagger) mlp_fwd3_tc_kernel<MODE, false, true><<<grid, kThreads3, smem, st>>>(pk, P, in, out);
+  else mlp_fwd3_tc_kernel<MODE, false, false><<<grid, kThreads3, smem, st>>>(pk, P, in, out);
   return finish_launch("mlp_fwd3_tc_kernel");
 }
 

@@ -25,10 +25,14 @@ def main():
     ap.add_argument("--img", type=int, default=64)
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--lr", type=float, default=5e-4)
+    ap.add_argument("--workload", default=None, help="take detector size, views and phantom from bench.WORKLOADS (e.g. config2)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
-    w = dict(img=args.img, thetas=[22.5 * i for i in range(8)], rays=args.rays, vol=128, L=4, H=128, enc="fourier")
-    pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], kind="ct", volume_res=w["vol"], device=dev)
+    w = dict(img=args.img, thetas=[22.5 * i for i in range(8)], rays=args.rays, vol=128, L=4, H=128, enc="fourier", kind="ct")
+    if args.workload:
+        w = dict(bench.WORKLOADS[args.workload], rays=args.rays)
+    pool, info = make_dataset(img_size=w["img"], thetas=w["thetas"], kind=w["kind"], volume_res=w["vol"], device=dev, weight_strategy="distance")
+    print(f"workload: {w['img']}x{w['img']} detector, {len(w['thetas']) + 1} views, phantom {w['kind']}, {w['rays']} rays/iteration, lr {args.lr}")
     res = {}
     for prec in ("fp32", "bf16"):
         torch.manual_seed(0)

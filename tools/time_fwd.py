@@ -39,8 +39,9 @@ def main():
     kw = dict(rays_o=o.contiguous(), rays_d=d.contiguous(), ray_idx=ri, t_starts=t0, t_ends=t1)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     outs = {}
-    for slots in ("2", "3"):
-        os.environ["ANGIO_FWD_SLOTS"] = slots
+    for slots in ("2", "3", "3s"):                 # "3s": three slots staggered over the layers (ANGIO_FWD_STAGGER=1, experiment)
+        os.environ["ANGIO_FWD_SLOTS"] = slots[0]
+        os.environ["ANGIO_FWD_STAGGER"] = "1" if slots.endswith("s") else "0"
         out = A.ops.mlp_forward(model._desc, model._flat, packed, A.ops.OUT_ALPHA, A.ops.PREC_BF16, **kw)
         torch.cuda.synchronize()
         ts = []
@@ -54,10 +55,10 @@ def main():
         ms = float(np.median(ts))
         tf = 139776 * n / (ms * 1e-3) * 1e-12
         outs[slots] = out.clone()
-        print(json.dumps({"slots": int(slots), "samples": n, "ms_median": ms, "ms_min": min(ts), "tflops_algorithmic": tf,
+        print(json.dumps({"slots": slots, "samples": n, "ms_median": ms, "ms_min": min(ts), "tflops_algorithmic": tf,
                           "frac_of_burst_peak": tf / peaks.get("bf16_tflops", 1590.0), "frac_of_sustained_peak": tf / peaks.get("bf16_tflops_sustained", 1400.0)}))
-    same = bool(outs["2"].equal(outs["3"]))
-    print("bit-identical outputs:", same, " max |diff|:", float((outs["2"] - outs["3"]).abs().max()))
+    same = bool(outs["2"].equal(outs["3"])) and bool(outs["2"].equal(outs["3s"]))
+    print("bit-identical outputs:", same, " max |diff|:", float((outs["2"] - outs["3"]).abs().max()), float((outs["2"] - outs["3s"]).abs().max()))
     sys.exit(0 if same else 1)
 
 
