@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(kThreads3, 1) mlp_fwd3_tc_kernel(const uint8_t
     const uint32_t idesc = make_idesc_bf16(kTile, kH, 0, 0);
     const uint32_t smem_base = smem_u32(smem);
     const int k0_steps = P.k0_pad / 16;
-    // STAGGER (experiment, ANGIO_FWD_STAGGER=1): slot s runs `lead` throw-away first-layer groups before its first tile and the
+    // STAGGER (default; ANGIO_FWD_STAGGER=0 switches it off): slot s runs `lead` throw-away first-layer groups before its first tile and the
     // slots that finish first append such groups at the end, so the three slots work on different layers of their tiles while
     // every slot still issues a group on every turn (the region rotation depends on that).
     const int lead = STAGGER ? (s * n_stages) / kSlots3 : 0;
@@ -1291,7 +1291,7 @@ static int launch_fwd3(const TcPlan& P, const void* packed, const angio_samples&
   const size_t smem = (size_t)P.total_bytes + 1024;
   const bool trace = getenv("ANGIO_TRACE") != nullptr;      // tools/trace_fwd.py: the instantiation with clock stamps
   const char* sg = getenv("ANGIO_FWD_STAGGER");
-  const bool stagger = sg && sg[0] == '1';                  // experiment: slots on different layers
+  const bool stagger = !(sg && sg[0] == '0');               // default: slots staggered over the layers; ANGIO_FWD_STAGGER=0: lock step
   static size_t cached[3] = {0, 0, 0};
   if (int rc = trace ? ensure_smem(mlp_fwd3_tc_kernel<MODE, true, false>, smem, &cached[0])
              : stagger ? ensure_smem(mlp_fwd3_tc_kernel<MODE, false, true>, smem, &cached[1])

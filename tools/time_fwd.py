@@ -39,7 +39,7 @@ def main():
     kw = dict(rays_o=o.contiguous(), rays_d=d.contiguous(), ray_idx=ri, t_starts=t0, t_ends=t1)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     outs = {}
-    for slots in ("2", "3", "3s"):                 # "3s": three slots staggered over the layers (ANGIO_FWD_STAGGER=1, experiment)
+    for slots in ("2", "3", "3s"):                 # "3": three slots in lock step, "3s": staggered over the layers (the default)
         os.environ["ANGIO_FWD_SLOTS"] = slots[0]
         os.environ["ANGIO_FWD_STAGGER"] = "1" if slots.endswith("s") else "0"
         out = A.ops.mlp_forward(model._desc, model._flat, packed, A.ops.OUT_ALPHA, A.ops.PREC_BF16, **kw)
