@@ -34,6 +34,24 @@ def allreduce_mean_gradient(flat_grad: torch.Tensor, local_batch: int, group=Non
     return int(n.item())
 
 
+def evaluate_sharded(fn, x: torch.Tensor, rank: int, world_size: int, group=None, out: torch.Tensor = None):
+    """fn(x) for a row-wise function fn, evaluated as world_size contiguous slices -- rank r computes rows
+    [r * chunk, (r + 1) * chunk) with chunk = ceil(n / world_size) -- and all-gathered, so every rank gets the full result
+    having done 1/world_size of the work (the occupancy-grid refresh of data-parallel training: every rank draws the same cells
+    and jitter, the per-row result does not depend on which rank computed it).  `out` (optional): a buffer of at least
+    chunk * world_size elements to gather into.  Returns a view of n elements."""
+    n = x.shape[0]
+    chunk = (n + world_size - 1) // world_size
+    lo = min(rank * chunk, n)
+    hi = min(lo + chunk, n)
+    full = out[:chunk * world_size] if out is not None else torch.empty(chunk * world_size, dtype=torch.float32, device=x.device)
+    mine = torch.zeros(chunk, dtype=torch.float32, device=x.device)
+    if hi > lo:
+        mine[:hi - lo] = fn(x[lo:hi]).reshape(-1)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n]
+
+
 def gather_concat(local: torch.Tensor, group=None, dst: int = 0):
     """Concatenate per-rank tensors (ragged along dim 0) on rank `dst`; other ranks get None."""
     rank, ws = world()

@@ -141,18 +141,12 @@ class Trainer:
         n = x.shape[0]
         if self.world == 1 or not self.shard_grid or n < self.world:
             return ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x)
+        from .distributed import evaluate_sharded
         chunk = (n + self.world - 1) // self.world
-        lo = min(self.rank * chunk, n)
-        hi = min(lo + chunk, n)
-        full = self.pool_bufs.typed("occ_gather", chunk * self.world, torch.float32, self.dev)
-        mine = full[self.rank * chunk:(self.rank + 1) * chunk]
-        if hi > lo:
-            ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id, points=x[lo:hi],
-                            out=mine[:hi - lo])
-        if hi - lo < chunk:
-            mine[hi - lo:].zero_()
-        torch.distributed.all_gather_into_tensor(full, mine.clone(), group=self.pg)
-        return full[:n]
+        return evaluate_sharded(lambda xs: ops.mlp_forward(self.model._desc, self.kflat, self.packed, ops.OUT_SIGMA, self.model._precision_id,
+                                                           points=xs),
+                                x, self.rank, self.world, group=self.pg,
+                                out=self.pool_bufs.typed("occ_gather", chunk * self.world, torch.float32, self.dev))
 
     def update_grids(self):
         """acc_update_n_step for both grids (run_nerf_acc.py:285-286)."""

@@ -29,6 +29,18 @@ def _worker(rank, world_size, port, tmpdir):
         assert torch.equal(got[:3, 0], torch.arange(3.0)) and float(got[3, 0]) == 100.0
     else:
         assert got is None
+    # ---- sharded evaluation (the occupancy-grid refresh of data-parallel training): every rank evaluates 1/world of the rows and
+    #      all-gathers -- identical to evaluating everything, for row counts that do and do not divide by the world size
+    from nerf_for_angiography_b200.distributed import evaluate_sharded
+    for n in (1, 7, 64, 1001):
+        x = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3) * 0.01
+        calls = []
+        fn = lambda xs: (calls.append(xs.shape[0]), torch.sin(xs).sum(-1))[1]          # noqa: E731
+        got = evaluate_sharded(fn, x, rank, world_size)
+        assert torch.equal(got, torch.sin(x).sum(-1)) and got.shape == (n,)
+        assert sum(calls) <= (n + world_size - 1) // world_size                        # this rank only did its share
+        buf = torch.full((2 * ((n + 1) // 2) + 5,), -1.0)
+        assert torch.equal(evaluate_sharded(fn, x, rank, world_size, out=buf), got)
     # ---- data-parallel gradient == single-process gradient on the concatenated batch (oracle math, fp32)
     roi = np.array([-100, -100, -100, 100, 100, 100], np.float32)
     grid = nerfacc_ref.OccupancyGrid(roi, 16); grid.binary[:] = True; grid.occs[:] = 0.05
