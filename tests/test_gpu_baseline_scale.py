@@ -401,3 +401,28 @@ def test_sampler_inclusion_frequency_per_ray(A):
     z = np.abs(f_gpu - f_ref) / sigma
     assert z.max() <= 6.0, (z.max(), int(z.argmax()))
     assert abs(f_gpu.sum() - n) < 1e-6 and np.corrcoef(f_gpu, f_ref)[0, 1] > 0.995
+
+
+def test_two_phase_visibility_8x256_at_config_scale(A):
+    """the width-256 kernels (config 4's 8 x 256 network) in the visibility pass at batch size: index-list + device-count
+    evaluation of the first 32 samples / the rays still alive == evaluating every marched sample, bit for bit (65 536 rays,
+    128^3 grid)"""
+    pool, info = _dataset("config3")
+    binary = torch.from_numpy(_grid_fill("phantom", info["volume"])).cuda()
+    o, d, _ = _draw(pool, 65536, seed=6)
+    p = ocppn.init_params(8, 256, "fourier", 5, 5.0, seed=5)
+    p["output_linear.0.bias"] = p["output_linear.0.bias"] - 4.0
+    m = A.CPPN(_mdef("bf16", L=8, H=256))
+    m.load_state_dict({**p, "img1": torch.zeros(2), "img2": torch.zeros(2)})
+    m = m.to("cuda"); m._ensure_flat()
+    packed = A.ops.mlp_pack(m._desc, m._flat)
+    step = (FAR - NEAR) / STEPS
+    ri, t0, t1, off = A.ops.march(o, d, ROI, ROI, RES, binary, NEAR, FAR, step)
+    kw = dict(rays_o=o, rays_d=d, ray_idx=ri, t_starts=t0, t_ends=t1)
+    full = A.ops.mlp_forward(m._desc, m._flat, packed, A.ops.OUT_ALPHA, A.ops.PREC_BF16, **kw)
+    two, evaluated = A.ops.alphas_two_phase(m._desc, m._flat, packed, A.ops.PREC_BF16, o, d, ri, t0, t1, off, 1e-2, k0=32)
+    a = A.ops.visibility_compact(full, off, t0, t1, 1e-2, 1e-4)
+    b = A.ops.visibility_compact(two, off, t0, t1, 1e-2, 1e-4)
+    assert a[0].numel() > 0 and sum(evaluated.tolist()) <= ri.numel()
+    for x, y in zip(a[:4], b[:4]):
+        assert x.equal(y)
