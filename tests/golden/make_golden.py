@@ -49,6 +49,7 @@ def main():
 
     # ---------------------------------------------------------------- geometry (a1, a2)
     geo = {}
+    write_geometry = not any(a.startswith("--only=") for a in sys.argv[1:])
     cases = [(0.0, 0.0, 0.0, 16, 12, 120.0, (0, 0, 0)),
              (45.0, 0.0, 0.0, 12, 16, 90.0, (0, 0, 0)),
              (135.0, 135.0, 0.0, 10, 10, 75.0, (0, 0, 0)),
@@ -62,11 +63,15 @@ def main():
         geo[f"c{ci}_o"] = o.numpy().astype(np.float64)
         geo[f"c{ci}_d"] = d.numpy().astype(np.float64)
     geo["n_cases"] = np.array(len(cases))
-    np.savez_compressed(os.path.join(OUT, "geometry.npz"), **geo)
+    if write_geometry:
+        np.savez_compressed(os.path.join(OUT, "geometry.npz"), **geo)
 
     # ---------------------------------------------------------------- CPPN (a9) fwd + grads
+    only = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--only=")]      # e.g. --only=cppn_fourier_2x256
     for tag, pos_enc, L, Hd in [("none_2x64", "none", 2, 64), ("fourier_4x128", "fourier", 4, 128),
-                                ("fourier_2x64", "fourier", 2, 64)]:
+                                ("fourier_2x64", "fourier", 2, 64), ("fourier_2x256", "fourier", 2, 256)]:
+        if only and f"cppn_{tag}" not in only:
+            continue
         torch.manual_seed(0)
         params = {'num_early_layers': L, 'num_late_layers': 0, 'num_filters': Hd, 'num_input_channels': 3,
                   'num_output_channels': 1, 'num_input_channels_views': 0, 'use_bias': True, 'pos_enc': pos_enc,
@@ -86,6 +91,8 @@ def main():
             if v.grad is not None:
                 out["grad:" + k] = v.grad.numpy()
         np.savez_compressed(os.path.join(OUT, f"cppn_{tag}.npz"), **out)
+    if only:
+        return
 
     # ---------------------------------------------------------------- CPPN with BARF encoding (f4): forward + grads at several alphas
     torch.manual_seed(0)

@@ -24,7 +24,7 @@ def test_geometry_bit_exact(golden_dir):
         assert np.array_equal(d, g[f"c{ci}_d"])          # float64, bit for bit
 
 
-@pytest.mark.parametrize("tag,pos_enc", [("none_2x64", "none"), ("fourier_4x128", "fourier"), ("fourier_2x64", "fourier")])
+@pytest.mark.parametrize("tag,pos_enc", [("none_2x64", "none"), ("fourier_4x128", "fourier"), ("fourier_2x64", "fourier"), ("fourier_2x256", "fourier")])
 def test_cppn_forward_and_grads(golden_dir, tag, pos_enc):
     g = _load(golden_dir, f"cppn_{tag}.npz")
     params = {k[3:]: torch.from_numpy(g[k]).clone().requires_grad_(True) for k in g.files if k.startswith("sd:")}
