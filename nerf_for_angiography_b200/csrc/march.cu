@@ -9,6 +9,8 @@
 // lockstep.  The write pass stages each ray's samples in shared memory and the whole warp flushes one ray
 // segment at a time, so global stores are contiguous 128-byte runs instead of 32 scattered 4-byte stores.
 // The 128^3 byte grid (2 MB) stays L2-resident; output is 12 B/sample (int32 ray id + t0 + t1).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -113,6 +115,31 @@ struct Marcher {
   }
 };
 
+// ---- closed form of the marcher's t-chain.  Inside a run the marcher walks t0 <- t1, t1 <- fl(t0 + dt) serially.  When every
+// value of a ray's chain lies in ONE binade [2^e, 2^(e+1)) all of them are multiples of u = 2^(e-23), and fl(x + dt) = x + r*u with
+// r = round(dt / u) the SAME for every x (the rounding could only depend on x if dt / u ended in exactly .5, which is excluded
+// below).  Sample k >= 1 of a run that starts with (t0_s, t1_s) is then (t1_s + (k-1) D, t1_s + k D) with D = r*u -- products and
+// sums of small integers times u, exact in fp32 -- so the write pass can compute every sample independently instead of replaying
+// the chain one sample at a time per thread.  Rays outside the guard (other geometry) keep the serial replay: bit-identical
+// either way.
+__device__ __forceinline__ bool linear_chain(float t_lo, float t_hi, float dt, float* delta) {
+  const uint32_t a = __float_as_uint(t_lo), b = __float_as_uint(t_hi);
+  const uint32_t e = a >> 23;                                       // sign + exponent
+  if (e != (b >> 23) || e == 0u || e >= 255u) return false;          // positive, normal, same binade
+  if (e < 24u) return false;
+  const float u = __uint_as_float((e - 23u) << 23);                  // ulp of the binade
+  const float s2 = __fmul_rn(__fdiv_rn(dt, u), 2.0f);                // 2 dt / u: scaling by powers of two is exact
+  if (!(s2 < 8388608.0f)) return false;                              // dt must be small against the binade (else s2 is not exact)
+  if (s2 == floorf(s2) && fmodf(s2, 2.0f) == 1.0f) return false;     // dt / u ends in .5: round-to-even would depend on x
+  *delta = __fsub_rn(__fadd_rn(t_lo, dt), t_lo);                     // = r * u, exact
+  return *delta > 0.0f;
+}
+
+// all values a ray's chain can take: run starts >= t_min - dt/2 (after a skip t0 = tm - dt/2), last t1 <= t_max + 2 dt
+__device__ __forceinline__ bool ray_chain_is_linear(float t_min, float t_max, float dt, float* delta) {
+  return linear_chain(__fsub_rn(t_min, dt), __fadd_rn(t_max, __fmul_rn(2.0f, dt)), dt, delta);
+}
+
 struct Aabb6 { float v[6]; };
 constexpr int kMaxRuns = 8;   // recorded runs per ray (count pass -> write pass)
 
@@ -123,7 +150,7 @@ __global__ void __launch_bounds__(128) march_count_kernel(const float* __restric
                                                           float* __restrict__ t_max, int32_t* __restrict__ counts,
                                                           float* __restrict__ run_t0, float* __restrict__ run_t1,
                                                           int32_t* __restrict__ run_n, int32_t* __restrict__ n_runs,
-                                                          const uint8_t* __restrict__ resume_alive) {
+                                                          const uint8_t* __restrict__ resume_alive, int skip_linear) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_rays) return;
   float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
@@ -141,6 +168,10 @@ __global__ void __launch_bounds__(128) march_count_kernel(const float* __restric
     b = b > far_plane ? far_plane : b;    // torch.clamp(t_max, max=far_plane)
     t_min[i] = a;
     t_max[i] = b;
+  }
+  if (skip_linear) {                      // counted by march_count_warp_kernel (one warp per ray, closed-form t-chain)
+    float delta;
+    if (ray_chain_is_linear(a, b, p.dt, &delta)) return;
   }
   Marcher m;
   m.init(o, d, a, b, p.dt);
@@ -176,6 +207,152 @@ __global__ void __launch_bounds__(128) march_count_kernel(const float* __restric
   if (n_runs) n_runs[i] = nr <= kMaxRuns ? nr : -1;
 }
 
+// Count pass, one WARP per ray, for rays whose t-chain is linear (linear_chain): the 32 lanes test 32 CONSECUTIVE candidate samples
+// at once -- candidate k of a stretch that starts with (T0, T1) is (T1 + (k-1) D, T1 + k D), its midpoint and grid lookup are
+// independent of the others -- and a ballot finds the first candidate that is empty or behind t_max.  Empty space is skipped with
+// the same closed form: the serial marcher adds dt to the midpoint until it reaches the next voxel boundary, i.e. j =
+// ceil((target - tm) / D) steps in exact integer arithmetic on multiples of the binade's ulp.  Emits exactly the counts and the
+// run table of march_count_kernel (which skips the rays counted here); 65 536 serial rays are only 14 warps per SM.
+__global__ void __launch_bounds__(256) march_count_warp_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                                                               int64_t n_rays, MarchParams p, const uint8_t* __restrict__ binary,
+                                                               const float* __restrict__ t_min, const float* __restrict__ t_max,
+                                                               int32_t* __restrict__ counts, float* __restrict__ run_t0,
+                                                               float* __restrict__ run_t1, int32_t* __restrict__ run_n,
+                                                               int32_t* __restrict__ n_runs, const uint8_t* __restrict__ resume_alive) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  for (int64_t i = warp_global; i < n_rays; i += n_warps) {
+    if (resume_alive && !resume_alive[i]) continue;         // march_count_kernel writes the zero count
+    const float o[3] = {rays_o[i * 3], rays_o[i * 3 + 1], rays_o[i * 3 + 2]};
+    const float d[3] = {rays_d[i * 3], rays_d[i * 3 + 1], rays_d[i * 3 + 2]};
+    const float ta = t_min[i], tb = t_max[i];              // stored by march_count_kernel (launched before, same stream)
+    float D;
+    if (!ray_chain_is_linear(ta, tb, p.dt, &D)) continue;   // left to the serial kernel
+    const float u = __uint_as_float(((__float_as_uint(ta) >> 23) - 23u) << 23);      // ulp of the ray's binade
+    const int Di = __float2int_rn(__fdiv_rn(D, u));         // D / u, exact
+    float inv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) inv[k] = __fdiv_rn(1.0f, d[k]);
+    const float h = __fmul_rn(p.dt, 0.5f);
+    float T0 = ta, T1 = __fadd_rn(ta, p.dt);                // the stretch's first candidate and its midpoint
+    float TM = __fmul_rn(__fadd_rn(T0, T1), 0.5f);
+    int total = 0, nr = 0, cur = 0;
+    bool open = false;
+    while (true) {
+      // candidate `lane` of the stretch
+      float c0 = T0, c1 = T1;
+      if (lane > 0) {
+        c0 = __fadd_rn(T1, __fmul_rn((float)(lane - 1), D));
+        c1 = __fadd_rn(T1, __fmul_rn((float)lane, D));
+      }
+      const float tm = lane > 0 ? __fmul_rn(__fadd_rn(c0, c1), 0.5f) : TM;
+      const bool active = tm < tb;
+      bool occ = false;
+      if (active) {
+        const float x = __fadd_rn(o[0], __fmul_rn(tm, d[0]));
+        const float y = __fadd_rn(o[1], __fmul_rn(tm, d[1]));
+        const float z = __fadd_rn(o[2], __fmul_rn(tm, d[2]));
+        occ = occupied_at(x, y, z, p, binary);
+      }
+      const unsigned stop = __ballot_sync(0xffffffffu, !occ);
+      const int f = stop ? __ffs(stop) - 1 : 32;            // candidates 0 .. f-1 are samples
+      if (f > 0) {
+        if (!open) {
+          open = true;
+          cur = 0;
+          if (lane == 0 && run_t0 && nr < kMaxRuns) { run_t0[(int64_t)nr * n_rays + i] = T0; run_t1[(int64_t)nr * n_rays + i] = T1; }
+        }
+        cur += f;
+        total += f;
+      }
+      if (f == 32) {                                        // the stretch goes on: candidate 32 becomes candidate 0
+        T0 = __fadd_rn(T1, __fmul_rn(31.0f, D));
+        T1 = __fadd_rn(T1, __fmul_rn(32.0f, D));
+        TM = __fmul_rn(__fadd_rn(T0, T1), 0.5f);
+        continue;
+      }
+      const float tm_f = __shfl_sync(0xffffffffu, tm, f);
+      if (!(tm_f < tb)) break;                              // candidate f lies behind t_max: the ray is done
+      // candidate f is empty: skip to the next voxel boundary in steps of dt (Marcher::advance, else-branch)
+      const float x = __fadd_rn(o[0], __fmul_rn(tm_f, d[0]));
+      const float y = __fadd_rn(o[1], __fmul_rn(tm_f, d[1]));
+      const float z = __fadd_rn(o[2], __fmul_rn(tm_f, d[2]));
+      const float tx = axis_dist(x, d[0], inv[0], p.roi.lo[0], p.ext[0], p.resf);
+      const float ty = axis_dist(y, d[1], inv[1], p.roi.lo[1], p.ext[1], p.resf);
+      const float tz = axis_dist(z, d[2], inv[2], p.roi.lo[2], p.ext[2], p.resf);
+      const float t = fmaxf(fminf(fminf(tx, ty), tz), 0.0f);
+      const float target = __fadd_rn(tm_f, t);
+      if (open) {
+        if (lane == 0 && run_n && nr < kMaxRuns) run_n[(int64_t)nr * n_rays + i] = cur;
+        ++nr;
+        open = false;
+      }
+      // serial: _t = tm; do { _t += dt } while (_t < target).  The loop ends at the first _t >= target; every _t >= t_max ends the
+      // ray whatever its exact value, so a target at / behind t_max (or not finite) needs no arithmetic at all.
+      if (!(target < tb)) break;
+      const int diff = __float2int_rn(__fdiv_rn(__fsub_rn(target, tm_f), u));        // (target - tm) / u, exact: same binade
+      int j = (diff + Di - 1) / Di;
+      if (j < 1) j = 1;
+      const float tm_new = __fadd_rn(tm_f, __fmul_rn((float)j, D));
+      TM = tm_new;                                          // after a skip the midpoint is the walked value itself
+      T0 = __fsub_rn(tm_new, h);
+      T1 = __fadd_rn(tm_new, h);
+    }
+    if (open) {
+      if (lane == 0 && run_n && nr < kMaxRuns) run_n[(int64_t)nr * n_rays + i] = cur;
+      ++nr;
+    }
+    if (lane == 0) {
+      counts[i] = total;
+      if (n_runs) n_runs[i] = nr <= kMaxRuns ? nr : -1;
+    }
+  }
+}
+
+// Write pass from the run table, one WARP per ray, every sample computed independently (see linear_chain): 32 consecutive
+// samples per store instruction, no shared-memory staging, no serial replay.  Rays whose chain is not linear or that have more
+// than kMaxRuns runs are left to march_write_kernel (which skips the rays handled here).
+__global__ void __launch_bounds__(256) march_write_runs_kernel(int64_t n_rays, float dt, const float* __restrict__ t_min,
+                                                               const float* __restrict__ t_max, const int32_t* __restrict__ offsets,
+                                                               const float* __restrict__ run_t0, const float* __restrict__ run_t1,
+                                                               const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs,
+                                                               int64_t capacity, int32_t* __restrict__ ray_idx,
+                                                               float* __restrict__ t_starts, float* __restrict__ t_ends) {
+  const int lane = threadIdx.x % 32;
+  const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+  const int64_t n_warps = (int64_t)gridDim.x * blockDim.x / 32;
+  for (int64_t i = warp_global; i < n_rays; i += n_warps) {
+    const int nr = n_runs[i];
+    const int base = offsets[i], total = offsets[i + 1] - base;
+    if (nr <= 0 || total <= 0) continue;
+    float delta;
+    if (!ray_chain_is_linear(t_min[i], t_max[i], dt, &delta)) continue;
+    // run r covers output samples [start_r, start_r + len_r): at most kMaxRuns runs, their starts in registers
+    int start[kMaxRuns + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int r = 0; r < kMaxRuns; ++r) start[r + 1] = start[r] + (r < nr ? run_n[(int64_t)r * n_rays + i] : 0);
+    for (int j = lane; j < total; j += 32) {
+      int r = 0;
+#pragma unroll
+      for (int q = 1; q < kMaxRuns; ++q) r += (q < nr && j >= start[q]) ? 1 : 0;
+      const int k = j - start[r];
+      const float s0 = run_t0[(int64_t)r * n_rays + i], s1 = run_t1[(int64_t)r * n_rays + i];
+      float a = s0, b = s1;
+      if (k > 0) {
+        a = __fadd_rn(s1, __fmul_rn((float)(k - 1), delta));
+        b = __fadd_rn(s1, __fmul_rn((float)k, delta));
+      }
+      if ((int64_t)base + j < capacity) {                 // never write past the caller's arrays
+        ray_idx[base + j] = (int32_t)i;
+        t_starts[base + j] = a;
+        t_ends[base + j] = b;
+      }
+    }
+  }
+}
+
 constexpr int kStage = 32;            // samples staged per ray per round
 constexpr int kStagePad = kStage + 1; // +1 float: lanes writing the same slot hit different banks
 constexpr int kWarpsPerBlock = 4;
@@ -185,14 +362,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
     const uint8_t* __restrict__ binary, const float* __restrict__ t_min, const float* __restrict__ t_max,
     const int32_t* __restrict__ offsets, const float* __restrict__ run_t0, const float* __restrict__ run_t1,
     const int32_t* __restrict__ run_n, const int32_t* __restrict__ n_runs, int64_t capacity, int32_t* __restrict__ ray_idx,
-    float* __restrict__ t_starts, float* __restrict__ t_ends) {
+    float* __restrict__ t_starts, float* __restrict__ t_ends, int skip_linear) {
   __shared__ float s_t0[kWarpsPerBlock][32][kStagePad];
   __shared__ float s_t1[kWarpsPerBlock][32][kStagePad];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int64_t ray0 = (blockIdx.x * (int64_t)kWarpsPerBlock + warp) * 32;
   if (ray0 >= n_rays) return;
   const int64_t i = ray0 + lane;
-  const bool valid = i < n_rays;
+  bool valid = i < n_rays;
   Marcher m;
   int written = 0, base = 0;
   // replay state: run index, samples left in the current run, running t0
@@ -200,6 +377,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerBlock) march_write_kernel(
   float rt0 = 0.0f, rt1 = 0.0f;
   bool replay = false;
   m.tm = 1.0f; m.tmax = 0.0f;  // done
+  if (valid && skip_linear && n_runs && n_runs[i] >= 0) {
+    float delta;
+    if (ray_chain_is_linear(t_min[i], t_max[i], p.dt, &delta)) valid = false;      // written by march_write_runs_kernel
+  }
   if (valid) {
     base = offsets[i];
     nr = n_runs ? n_runs[i] : -1;
@@ -436,9 +617,24 @@ extern "C" int angio_march_count(const float* rays_o, const float* rays_d, int64
   if (n_rays == 0) return 0;
   Aabb6 aabb;
   for (int k = 0; k < 6; ++k) aabb.v[k] = aabb_host[k];
+  // ANGIO_MARCH_SERIAL_COUNT=1 keeps the thread-per-ray walk for every ray (A/B measurements; bit-identical output)
+  const char* ev = getenv("ANGIO_MARCH_SERIAL_COUNT");
+  const int fast = !(ev && ev[0] == '1') ? 1 : 0;
+  const MarchParams mp = make_params(roi_host, res, step_size);
+  // the serial kernel first: it stores t_min / t_max and the counts of the rays it keeps (and of rays that are not alive)
   angio::note_launch("march_count_kernel"); march_count_kernel<<<angio::blocks_for(n_rays, 128), 128, 0, angio::as_stream(stream)>>>(
-      rays_o, rays_d, n_rays, aabb, make_params(roi_host, res, step_size), binary, near_plane, far_plane, t_min, t_max, counts,
-      run_table_t0(runs, n_rays), run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays), resume_alive);
+      rays_o, rays_d, n_rays, aabb, mp, binary, near_plane, far_plane, t_min, t_max, counts,
+      run_table_t0(runs, n_rays), run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays), resume_alive, fast);
+  if (int rc = angio::finish_launch("angio_march_count")) return rc;
+  if (fast) {
+    int64_t blocks = (n_rays + 7) / 8;                    // 8 warps per block, one ray per warp per pass
+    const int64_t cap_blocks = (int64_t)angio::sm_count() * 32;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    angio::note_launch("march_count_warp_kernel");
+    march_count_warp_kernel<<<(int)blocks, 256, 0, angio::as_stream(stream)>>>(
+        rays_o, rays_d, n_rays, mp, binary, t_min, t_max, counts, run_table_t0(runs, n_rays),
+        run_table_t1(runs, n_rays), run_table_n(runs, n_rays), run_table_count(runs, n_rays), resume_alive);
+  }
   return angio::finish_launch("angio_march_count");
 }
 
@@ -477,11 +673,25 @@ extern "C" int angio_march_write(const float* rays_o, const float* rays_d, int64
   ANGIO_REQUIRE(n_rays >= 0 && res > 0 && step_size > 0.0f, "angio_march_write: bad sizes");
   if (n_rays == 0) return 0;
   const int rays_per_block = 32 * kWarpsPerBlock;
+  const int64_t cap = capacity > 0 ? capacity : INT64_MAX;
+  void* rt = const_cast<void*>(runs);
+  // ANGIO_MARCH_SERIAL_WRITE=1 keeps the serial replay for every ray (A/B measurements; bit-identical output)
+  const char* ev = getenv("ANGIO_MARCH_SERIAL_WRITE");
+  const int fast = (runs != nullptr && !(ev && ev[0] == '1')) ? 1 : 0;
+  if (fast) {
+    int64_t blocks = (n_rays + 7) / 8;                    // 8 warps per block, one ray per warp per pass
+    const int64_t cap_blocks = (int64_t)angio::sm_count() * 32;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    angio::note_launch("march_write_runs_kernel");
+    march_write_runs_kernel<<<(int)blocks, 256, 0, angio::as_stream(stream)>>>(n_rays, step_size, t_min, t_max, offsets, run_table_t0(rt, n_rays),
+                                                                               run_table_t1(rt, n_rays), run_table_n(rt, n_rays),
+                                                                               run_table_count(rt, n_rays), cap, ray_idx, t_starts, t_ends);
+    if (int rc = angio::finish_launch("march_write_runs_kernel")) return rc;
+  }
   angio::note_launch("march_write_kernel"); march_write_kernel<<<angio::blocks_for(n_rays, rays_per_block), rays_per_block, 0, angio::as_stream(stream)>>>(
       rays_o, rays_d, n_rays, make_params(roi_host, res, step_size), binary, t_min, t_max, offsets,
-      run_table_t0(const_cast<void*>(runs), n_rays), run_table_t1(const_cast<void*>(runs), n_rays),
-      run_table_n(const_cast<void*>(runs), n_rays), run_table_count(const_cast<void*>(runs), n_rays),
-      capacity > 0 ? capacity : INT64_MAX, ray_idx, t_starts, t_ends);
+      run_table_t0(rt, n_rays), run_table_t1(rt, n_rays), run_table_n(rt, n_rays), run_table_count(rt, n_rays),
+      cap, ray_idx, t_starts, t_ends, fast);
   return angio::finish_launch("angio_march_write");
 }
 

@@ -120,6 +120,34 @@ def test_march_bit_exact(A, fill):
         assert len(gi) > 100 * len(o) * 0.5
 
 
+@pytest.mark.parametrize("dist,n_steps", [(1000.0, 300), (1000.0, 77), (60.0, 300), (2100.0, 500)])
+def test_march_bit_exact_across_binades(A, dist, n_steps, monkeypatch):
+    """The warp-per-ray count / write kernels use the closed form of the t-chain only for rays whose whole chain lies in one fp32
+    binade; at these source distances [t_min, t_max] straddles 1024 / 64 / 2048, so some rays take the closed form and the others
+    the serial walk -- all of them bit-equal to the oracle, and to the all-serial kernels (ANGIO_MARCH_SERIAL_*)."""
+    res = 32
+    rng = np.random.default_rng(11)
+    binary = rng.random((res,) * 3) < 0.35
+    W = 32
+    half = 100.0 if dist > 200 else 30.0
+    os_, ds_ = [], []
+    for th, ph in ((0.0, 0.0), (45.0, 10.0), (135.0, 135.0)):
+        o, d, _ = ogeo.get_ray_values(th, ph, 0.0, [0, 0, dist], W, W, (W / 2) * dist / half)
+        os_.append(o.reshape(-1, 3)); ds_.append(d.reshape(-1, 3))
+    o = np.concatenate(os_).astype(np.float32); d = np.concatenate(ds_).astype(np.float32)
+    aabb = np.array([-half] * 3 + [half] * 3, np.float32)
+    near, far = dist - half, dist + half
+    (ri, ts, te, off), (gi, g0, g1, goff) = _march_both(A, o, d, binary, res, near=near, far=far, n_steps=n_steps, aabb=aabb)
+    assert np.array_equal(goff.astype(np.int64), off) and np.array_equal(gi.astype(np.int64), ri)
+    assert np.array_equal(g0, ts) and np.array_equal(g1, te)
+    assert len(gi) > 0
+    monkeypatch.setenv("ANGIO_MARCH_SERIAL_COUNT", "1")
+    monkeypatch.setenv("ANGIO_MARCH_SERIAL_WRITE", "1")
+    step = np.float32((far - near) / n_steps)
+    si, s0, s1, soff = A.ops.march(_dev(o), _dev(d), aabb, aabb, res, _dev(binary), near, far, float(step))
+    assert np.array_equal(si.cpu().numpy(), gi) and np.array_equal(s0.cpu().numpy(), g0) and np.array_equal(s1.cpu().numpy(), g1)
+
+
 def test_march_degenerate_rays(A):
     """axis-parallel directions (zero components -> inf / NaN in the slab test), rays missing the box, zero rays"""
     res = 16
