@@ -39,7 +39,7 @@ constexpr int kActBytes = 65536;    // a_d / delta_d tile image: four [128 x 64]
 constexpr int kMaskBytes = 4096;    // ReLU bit mask of one a_d tile: [128 rows][8 x 32 bits]
 constexpr int kStageBytes = 8 * 4096;
 constexpr float kTwoPi = 6.2831855f;
-constexpr uint32_t kColD = 0, kColA = 256, kColA0 = 384;   // TMEM columns
+constexpr uint32_t kColD = 0, kColA = 256;   // TMEM columns of the dgrad pipeline (the forward uses two 256-column regions)
 
 struct Plan256 {
   int n_hidden, basis, k0, k0_pad;
@@ -120,7 +120,8 @@ struct __align__(8) Bars256 {
   uint64_t full[kRing];
   uint64_t empty[kRing];
   uint64_t c_ready;      // constant block landed
-  uint64_t a_ready;      // A operand (or features) of the next stage written by all 8 epilogue warps
+  uint64_t a_ready;      // (dgrad) A operand (or features) of the next stage written by all 8 epilogue warps
+  uint64_t a_pass[4];    // (forward) pass p of the epilogue done: 32 + 32 more features of the next A operand are in place
   uint64_t acc_ready;    // accumulator of the current stage complete
   uint32_t tmem_base;
 };
@@ -209,6 +210,7 @@ __device__ __forceinline__ void pipe_setup(Bars256& bars, int warp) {
     for (int s = 0; s < kRing; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); }
     mbar_init(&bars.c_ready, 1);
     mbar_init(&bars.a_ready, 8);
+    for (int p = 0; p < 4; ++p) mbar_init(&bars.a_pass[p], 8);
     mbar_init(&bars.acc_ready, 1);
     fence_mbar_init();
   }
@@ -270,37 +272,69 @@ __global__ void __launch_bounds__(kThreads, 1) mlp256_fwd_kernel(const uint8_t* 
       for (int64_t j = 0; j < my_tiles; ++j)
         for (int c = 0; c < P.n_chunks_fwd; ++c, ++it) {
           const int slot = it % kRing;
+          // MMA order of a hidden layer's K-chunks: 0, 2, 1, 3 (the two column halves of the epilogue finish chunks 0 and 2 first)
+          const int cc = c == 0 ? 0 : 1 + ((c - 1) & ~3) + (((c - 1) & 1) << 1) + (((c - 1) & 2) >> 1);
           mbar_wait(&bars.empty[slot], ((it / kRing) & 1) ^ 1);
           mbar_arrive_expect_tx(&bars.full[slot], kChunk);
-          bulk_g2s(ring + slot * kChunk, packed + (int64_t)c * kChunk, kChunk, &bars.full[slot]);
+          bulk_g2s(ring + slot * kChunk, packed + (int64_t)cc * kChunk, kChunk, &bars.full[slot]);
         }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // TMEM = two 256-column regions.  Stage g (global count over tiles and layers) accumulates into region g & 1 and reads its A
+    // operand from the other one, where the epilogue of stage g - 1 wrote it IN PLACE of the accumulator columns it had drained:
+    // hidden units [128 h + 32 p, +32) of pass p land in columns 128 h + 16 p .. +16 of that region.  The issuer follows the epilogue
+    // pass by pass (four k-steps = 2 x 32 features per pass), so a layer's MMAs overlap the previous layer's epilogue.
     const uint32_t idesc = make_idesc_bf16(kTile, kW, 0, 0);
     const uint32_t ring_base = smem_u32(ring);
-    uint32_t it = 0, a_phase = 0;
+    uint32_t it = 0, g = 0;
+    uint32_t phm = 0;                                          // bit p: parity the issuer waits for on a_pass[p]
     for (int64_t j = 0; j < my_tiles; ++j) {
-      for (int st = 0; st < n_stages; ++st) {
-        mbar_wait(&bars.a_ready, a_phase);
-        a_phase ^= 1;
-        const int nch = st == 0 ? 1 : 4;
-        for (int c = 0; c < nch; ++c, ++it) {
+      for (int st = 0; st < n_stages; ++st, ++g) {
+        const uint32_t d_col = (g & 1) * 256, a_reg = ((g & 1) ^ 1) * 256;
+        if (st == 0) {
+          mbar_wait(&bars.a_pass[0], phm & 1u); phm ^= 1u;
           const int slot = it % kRing;
           mbar_wait(&bars.full[slot], (it / kRing) & 1);
           fence_after_sync();
           if (lane == 0) {
             const uint32_t wbase = ring_base + slot * kChunk;
-            const int ksteps = st == 0 ? P.k0_pad / 16 : 4;
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t a_col = st == 0 ? kColA0 + k * 8 : kColA + (c * 4 + k) * 8;
-              mma_ts(kColD, a_col, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, (c | k) != 0);
+            for (int k = 0; k < P.k0_pad / 16; ++k)               // feature chunk k: columns 128 (k & 1) + 8 (k / 2)
+              mma_ts(d_col, a_reg + (k & 1) * 128 + (k >> 1) * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc, k != 0);
+            mma_commit(&bars.empty[slot]);
+            mma_commit(&bars.acc_ready);
+          }
+          __syncwarp();
+          ++it;
+          continue;
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          mbar_wait(&bars.a_pass[p], (phm >> p) & 1u); phm ^= 1u << p;
+          const uint32_t i0 = it + (p >> 1) * 2;                   // ring entries of K-chunks (p / 2) and 2 + (p / 2)
+          const int slot0 = i0 % kRing, slot1 = (i0 + 1) % kRing;
+          if ((p & 1) == 0) {
+            mbar_wait(&bars.full[slot0], (i0 / kRing) & 1);
+            mbar_wait(&bars.full[slot1], ((i0 + 1) / kRing) & 1);
+          }
+          fence_after_sync();
+          if (lane == 0) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t wbase = ring_base + (hh ? slot1 : slot0) * kChunk;
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const int k = 2 * (p & 1) + kk;                     // k-step inside the 64-feature chunk
+                mma_ts(d_col, a_reg + hh * 128 + p * 16 + kk * 8, make_smem_desc_sw128(wbase + k * 32, 16, 1024), idesc,
+                       (p | hh | kk) != 0);
+              }
             }
-            mma_commit(&bars.empty[slot]);                 // ring slot is free once these MMAs have read it
-            if (c == nch - 1) mma_commit(&bars.acc_ready);
+            if (p & 1) { mma_commit(&bars.empty[slot0]); mma_commit(&bars.empty[slot1]); }
+            if (p == 3) mma_commit(&bars.acc_ready);
           }
           __syncwarp();
         }
+        it += 4;
       }
     }
   } else {
@@ -309,9 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp256_fwd_kernel(const uint8_t* 
     const int h = (warp - 2) / 4;                 // column half: hidden units [128 h, 128 h + 128)
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    const uint32_t acc_col = kColD + lane_off + h * 128;
-    const uint32_t a_col = kColA + lane_off + h * 64;
-    const uint32_t a0_col = kColA0 + lane_off;
+    const uint32_t half_col = lane_off + h * 128;   // this warp's 128 columns inside either region: accumulator in, next A operand out
     mbar_wait(&bars.c_ready, 0);
     const float* coef = consts + (L + 2) * kW + 4;
     const float b_out = consts[(L + 2) * kW];
@@ -334,54 +366,65 @@ __global__ void __launch_bounds__(kThreads, 1) mlp256_fwd_kernel(const uint8_t* 
       }
       idx = ii;
     };
-    auto encode = [&](int64_t jt, const float (&xx)[3]) {        // the two halves split the 8-word chunks of a_0 (chunk c8 -> half c8 & 1)
+    // Features of a tile: the two column halves split the 16-column K chunks of a_0 (chunk c8 -> half c8 & 1); this warp's chunks
+    // c8 = h and h + 2 are kept in registers and stored to columns [0, 16) of its half of a region once those are free.
+    uint32_t feat[2][8];
+    auto encode = [&](int64_t jt, const float (&xx)[3]) {
       const int64_t tl = blockIdx.x + jt * gridDim.x;
       uint8_t* a0_row = TRAIN ? saved + tl * kA0Bytes + row * 128 : nullptr;
 #pragma unroll
-      for (int c8 = 0; c8 < 4; ++c8) {
-        if ((c8 & 1) != h) continue;
-        uint32_t v8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (c8 * 16 < P.k0_pad) {
-          encode_feature_chunk(xx, coef, nb, c8, v8);
-          tmem_st8(a0_col + c8 * 8, v8);
-        }
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int c8 = 2 * c2 + h;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) feat[c2][e] = 0u;
+        if (c8 * 16 < P.k0_pad) encode_feature_chunk(xx, coef, nb, c8, feat[c2]);
         if (TRAIN) {
-          *reinterpret_cast<uint4*>(a0_row + (((2 * c8) ^ (row & 7)) << 4)) = make_uint4(v8[0], v8[1], v8[2], v8[3]);
-          *reinterpret_cast<uint4*>(a0_row + (((2 * c8 + 1) ^ (row & 7)) << 4)) = make_uint4(v8[4], v8[5], v8[6], v8[7]);
+          *reinterpret_cast<uint4*>(a0_row + (((2 * c8) ^ (row & 7)) << 4)) = make_uint4(feat[c2][0], feat[c2][1], feat[c2][2], feat[c2][3]);
+          *reinterpret_cast<uint4*>(a0_row + (((2 * c8 + 1) ^ (row & 7)) << 4)) = make_uint4(feat[c2][4], feat[c2][5], feat[c2][6], feat[c2][7]);
         }
       }
+    };
+    auto store_features = [&](uint32_t region_col) {
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2)
+        if ((2 * c2 + h) * 16 < P.k0_pad) tmem_st8(region_col + half_col + c2 * 8, feat[c2]);
     };
     float xn[3], dtn;
     bool vn;
     int64_t in_;
     fetch(0, xn, dtn, vn, in_);
-    if (my_tiles > 0) { encode(0, xn); signal_ready(&bars.a_ready, lane); }
+    if (my_tiles > 0) { encode(0, xn); store_features(256); signal_ready(&bars.a_pass[0], lane); }   // stage 0 accumulates into region 0
+    uint32_t g = 0;
     for (int64_t j = 0; j < my_tiles; ++j) {
       const int64_t tile = blockIdx.x + j * gridDim.x;
       const int64_t i = in_;
       const bool valid = vn;
       const float dt = dtn;
       fetch(j + 1, xn, dtn, vn, in_);             // in flight during this tile's layers
-      for (int l = 0; l <= L; ++l) {
+      for (int l = 0; l <= L; ++l, ++g) {
         const bool last = l == L;
         const bool more = j + 1 < my_tiles;
-        if (last && more) encode(j + 1, xn);      // the feature region is free: stage 0 of this tile is long done
+        if (last && more) encode(j + 1, xn);      // sin / cos of the next tile while the last layer's MMAs run
         mbar_wait(&bars.acc_ready, phase);
         phase ^= 1;
         fence_after_sync();
         const float* bias = consts + l * kW + h * 128;
+        const uint32_t reg_col = (g & 1) * 256 + half_col;      // accumulator of this stage = A operand region of the next
         uint32_t ra[32], rb[32], pk[16];
         uint32_t mbits[4];
         float dot = 0.0f;
-        tmem_ld32(acc_col, ra);
+        tmem_ld32(reg_col, ra);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           wait_ld();
-          if (p < 3) { if (p & 1) tmem_ld32(acc_col + (p + 1) * 32, ra); else tmem_ld32(acc_col + (p + 1) * 32, rb); }   // next pass in flight
+          if (p < 3) { if (p & 1) tmem_ld32(reg_col + (p + 1) * 32, ra); else tmem_ld32(reg_col + (p + 1) * 32, rb); }   // next pass in flight
           if (last) dot = (p & 1) ? bias_relu_32<true>(rb, bias + p * 32, w_out + p * 32, pk, dot) : bias_relu_32<true>(ra, bias + p * 32, w_out + p * 32, pk, dot);
           else if (p & 1) bias_relu_32<false>(rb, bias + p * 32, nullptr, pk, 0.f);
           else bias_relu_32<false>(ra, bias + p * 32, nullptr, pk, 0.f);
-          if (!last) tmem_st16(a_col + p * 16, pk);
+          // in place: the 16 packed columns of pass p replace accumulator columns [16 p, 16 p + 16) of this warp's half, drained in
+          // passes <= p; after the last layer the next tile's features take columns [0, 16) instead
+          if (!last) { tmem_st16(reg_col + p * 16, pk); signal_ready(&bars.a_pass[p], lane); }
+          else if (p == 0 && more) { store_features((g & 1) * 256); signal_ready(&bars.a_pass[0], lane); }
           if (TRAIN) {
             if ((p & 1) == 0) stage_acquire(lane);
             stage_half_row(stage, lane, p & 1, pk);
@@ -389,8 +432,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp256_fwd_kernel(const uint8_t* 
             if (p & 1) flush_stage(stage, act_base + ((int64_t)l * lay_tiles + tile) * kActBytes + (2 * h + (p >> 1)) * 16384 + q * 4096, lane);
           }
         }
-        // hand the tile (or, after the last layer, the next tile) to the tensor core
-        if (!last || more) signal_ready(&bars.a_ready, lane);
         if (TRAIN)
           *reinterpret_cast<uint4*>(mask_base + (((int64_t)l * lay_tiles + tile) * kTile + row) * 32 + h * 16) = make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]);
         if (last) {

@@ -5,6 +5,7 @@ timeout 600 python bench.py > gpurun_out/r02_bench_config3_n1.json 2> gpurun_out
 timeout 900 python bench.py --workload config4 --advance 100 --repeats 3 --steps 10 > gpurun_out/r02_bench_config4_n1.json 2> gpurun_out/r02_bench_config4_n1.err; echo "rc=$?" >> gpurun_out/r02_bench_config4_n1.err
 timeout 600 python bench.py --workload config5 --steps 6 --repeats 3 > gpurun_out/r02_bench_config5_n1.json 2> gpurun_out/r02_bench_config5_n1.err; echo "rc=$?" >> gpurun_out/r02_bench_config5_n1.err
 timeout 300 python tools/time_fwd.py > gpurun_out/r02_fwd_two_vs_three_slots.log 2>&1
+timeout 200 python tools/time_fwd256.py > gpurun_out/r02_fwd256_isolated.log 2>&1
 timeout 120 python tools/trace_fwd.py > gpurun_out/r02_fwd3_pipeline_trace.txt 2>&1
 ARGS="--steps 2 --warmup 3 --repeats 1 --advance 300 --no-cpu-baseline"
 python bench.py $ARGS > gpurun_out/r02_ncu_plain.json 2> gpurun_out/r02_ncu_plain.err &&

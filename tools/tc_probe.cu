@@ -9,6 +9,7 @@
 //     4..7 throughput: 4 SS N=128, 5 TS N=128, 6 SS N=256, 7 TS N=256
 //     8  SS  bf16 inputs, D format F16 (is it legal? halves the accumulator drain)
 //     9  LDTM (tcgen05.ld) bandwidth: 4 / 8 warps reading 128 columns repeatedly
+//     10..13 CTA-pair throughput (cta_group::2, M = 256): 10 SS N=128, 11 TS N=128, 12 SS N=256, 13 TS N=256
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -143,6 +144,59 @@ __global__ void __launch_bounds__(128, 1) perf_kernel(int iters, int ts_mode, fl
 }
 
 
+// CTA-pair throughput (cta_group::2): M = 256 over two SMs (128 rows each), each CTA holds NN/2 rows of B; only the leader issues.
+// Per SM the FLOPs per instruction equal the single-CTA M = 128 case, but every SM reads half of the B operand.
+template <int NN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) perf_pair_kernel(int iters, int ts_mode, float* sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                 // 2 x 16 KB (K = 128), this CTA's 128 rows
+  uint8_t* sB = smem + 32768;         // NN/2 rows x 128 K: 2 blocks of (NN/2)*128 B
+  __shared__ uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x / 32;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  for (int i = threadIdx.x; i < (32768 + NN * 128) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (threadIdx.x == 0 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, NN, 0, 0);
+    for (int it = 0; it < iters; ++it) {
+      for (int k = 0; k < 8; ++k) {
+        uint32_t a_off = (k / 4) * 16384 + (k % 4) * 32;
+        uint32_t b_off = (k / 4) * (NN / 2 * 128) + (k % 4) * 32;
+        uint64_t da = make_smem_desc_sw128(smem_u32(sA) + a_off, 16, 1024);
+        uint64_t db = make_smem_desc_sw128(smem_u32(sB) + b_off, 16, 1024);
+        const uint32_t acc = k > 0;
+        if (ts_mode)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem), "r"(tmem + 256 + k * 8), "l"(db),
+                       "r"(idesc), "r"(acc) : "memory");
+        else
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                       : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(&bar_mma)), "h"((uint16_t)3) : "memory");
+  }
+  mbar_wait(&bar_mma, 0);
+  fence_after_sync();
+  if (threadIdx.x == 0 && sink) sink[blockIdx.x] = 1.0f;
+  fence_before_sync();
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // issue-cadence experiments (TS mode, K = 128 per accumulation group):
 //   mode 0: one issuer, one accumulator (baseline = variant 5)      mode 1: one issuer alternating two accumulators per k-step
 //   mode 2: two issuer warps, one accumulator each                  mode 3: one issuer, accumulate flag always 0 (no RAW chain)
@@ -257,6 +311,30 @@ int main(int argc, char** argv) {
   int variant = argc > 1 ? atoi(argv[1]) : 0;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s sm_%d%d SMs=%d variant=%d\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount, variant);
+
+  if (variant >= 10 && variant <= 13) {
+    const int NN = (variant >= 12) ? 256 : 128, ts = (variant & 1);
+    const int iters = 4096;
+    size_t smem = 32768 + NN * 128 + 1024;
+    const int blocks = prop.multiProcessorCount & ~1;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float ms = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      CK(cudaEventRecord(e0));
+      if (NN == 128) {
+        CK(cudaFuncSetAttribute(perf_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        perf_pair_kernel<128><<<blocks, 128, smem>>>(iters, ts, nullptr);
+      } else {
+        CK(cudaFuncSetAttribute(perf_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        perf_pair_kernel<256><<<blocks, 128, smem>>>(iters, ts, nullptr);
+      }
+      CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    double flops = 2.0 * 128 * NN * 16 * 8.0 * iters * blocks;
+    printf("PERF-PAIR variant=%d mode=%s M=256 N=%d: %.3f ms  %.1f TFLOP/s\n", variant, ts ? "TS" : "SS", NN, ms, flops / ms * 1e-9);
+    return 0;
+  }
 
   if (variant == 9) {
     for (int nw = 4; nw <= 8; nw += 4) {
