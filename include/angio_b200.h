@@ -81,11 +81,20 @@ ANGIO_API int angio_sample_candidates(const float* weights, int64_t n_pool, uint
  * (the `.sample(frac=1)` of nerf/nerf_helpers.py:139), all stream-ordered, no host sync.  ids_out: [n] int64 flat ray ids
  * (view * H * W + y * W + x).  status: 2 x int32 on the device: [0] = number of candidates, [1] = 1 if the candidate
  * buffer overflowed or held fewer than n rays (ids_out is then undefined; re-draw with a larger tau / capacity).
- * The permutation depends only on (seed, selected set): reproducible although candidates are appended in arbitrary order.
+ * The permutation depends only on (seed, selected set), and candidates whose key equals the n-th smallest are taken in ray-id
+ * order: the draw is a function of the seed although candidates are appended in arbitrary order.
  */
 ANGIO_API int64_t angio_sample_rays_workspace_bytes(int32_t capacity, int64_t n);
 ANGIO_API int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n, uint64_t seed, float tau, int32_t capacity,
                                 int64_t* ids_out, int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
+/* Check mode of the sampler (the second half of angio_sample_rays on caller-supplied candidates): the n candidates with the
+ * smallest keys -- positive fp32 race keys, e.g. pre-drawn Exp(1)/weight variates a numpy reference of
+ * DataFrame.sample(n, weights) (nerf/nerf_helpers.py:137-150) draws from the same uniforms -- shuffled as above.  Equal keys at
+ * the selection threshold are resolved by ray id (smallest first), so the drawn set depends on (keys, ids) alone.
+ * cand_keys / cand_ids: [m] on the device; workspace: angio_sample_rays_workspace_bytes(m, n).  status as above.
+ */
+ANGIO_API int angio_sample_select(const float* cand_keys, const int64_t* cand_ids, int32_t m, int64_t n, uint64_t seed,
+                                  int64_t* ids_out, int32_t* status, void* workspace, int64_t workspace_bytes, void* stream);
 /* angio_raygen in gather mode driven by flat ray ids (the sampler's output); pixels: [n_views, H, W] -> pix_out[n] */
 ANGIO_API int angio_raygen_flat(const double* cam2world, const int64_t* ids, int64_t n, int32_t img_w, int32_t img_h,
                                 double focal, const float* pixels, float* rays_o, float* rays_d, float* pix_out, void* stream);

@@ -37,6 +37,7 @@ PROTOTYPES = {
     "angio_sample_candidates": (c_i32, [c_ptr, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_sample_rays_workspace_bytes": (c_i64, [c_i32, c_i64]),
     "angio_sample_rays": (c_i32, [c_ptr, c_i64, c_i64, ctypes.c_uint64, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
+    "angio_sample_select": (c_i32, [c_ptr, c_ptr, c_i32, c_i64, ctypes.c_uint64, c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "angio_raygen_flat": (c_i32, [c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_raygen": (c_i32, [c_ptr, c_i32, c_ptr, c_ptr, c_ptr, c_i64, c_i32, c_i32, c_f64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "angio_march_runs_bytes": (c_i64, [c_i64]),

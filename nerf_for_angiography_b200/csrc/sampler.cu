@@ -145,11 +145,17 @@ __global__ void __launch_bounds__(kSelThreads) radix_hist_kernel(const float* __
 }
 
 // one CTA: the three bins -> threshold bit pattern + ties to take; also the status words of the call
+constexpr int kTieCap = 1024;
+
 __global__ void __launch_bounds__(kSelThreads) select_finish_kernel(int32_t* __restrict__ ctl, int32_t capacity, int32_t n,
-                                                                   const uint32_t* __restrict__ hists, int32_t* __restrict__ status,
-                                                                   int64_t* __restrict__ ids_out) {
+                                                                   uint32_t* __restrict__ hists, int32_t* __restrict__ status,
+                                                                   int64_t* __restrict__ ids_out, const float* __restrict__ cand_keys,
+                                                                   const int64_t* __restrict__ cand_ids) {
   __shared__ uint32_t s_scan[32];
   __shared__ uint32_t s_out[2];
+  __shared__ int64_t s_tie[kTieCap];
+  __shared__ uint32_t s_ntie;
+  __shared__ long long s_id_thr;
   const int count = ctl[0];
   const int m = min(count, capacity);
   if (threadIdx.x == 0) {
@@ -169,22 +175,64 @@ __global__ void __launch_bounds__(kSelThreads) select_finish_kernel(int32_t* __r
     need = s_out[1];
     __syncthreads();
   }
-  if (threadIdx.x == 0) { ctl[1] = (int32_t)prefix; ctl[2] = (int32_t)need; ctl[3] = 0; }
+  // Candidates whose key EQUALS the threshold: `need` of them belong to the draw.  With fp32 keys this is not a measure-zero event
+  // (about n * 2^-24 per draw: every few hundred draws at n = 65 536), and the candidate list is in atomic-append order, so the
+  // ties are resolved by ray id -- the `need` smallest ids -- which makes the drawn SET a function of the seed alone.
+  if (threadIdx.x == 0) { s_ntie = 0; s_id_thr = 0x7FFFFFFFFFFFFFFFll; }
+  __syncthreads();
+  const uint32_t* kb = reinterpret_cast<const uint32_t*>(cand_keys);
+  for (int i = threadIdx.x; i < m; i += kSelThreads)
+    if (kb[i] == prefix) {
+      const uint32_t p = atomicAdd(&s_ntie, 1u);
+      if (p < (uint32_t)kTieCap) s_tie[p] = cand_ids[i];
+    }
+  __syncthreads();
+  const uint32_t nt = s_ntie;
+  if (need < nt && nt <= (uint32_t)kTieCap) {
+    for (uint32_t t = threadIdx.x; t < nt; t += kSelThreads) {
+      const int64_t mine = s_tie[t];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < nt; ++j) rank += s_tie[j] < mine;
+      if (rank == need - 1) s_id_thr = mine;
+    }
+  } else if (need < nt) {
+    // thousands of equal keys (degenerate weights): bisect the smallest id threshold with count(tied ids <= threshold) >= need
+    long long lo = -1, hi = 0x3FFFFFFFFFFFFFFFll;
+    while (hi - lo > 1) {
+      const long long mid = lo + (hi - lo) / 2;
+      __syncthreads();
+      if (threadIdx.x == 0) s_ntie = 0;
+      __syncthreads();
+      uint32_t c = 0;
+      for (int i = threadIdx.x; i < m; i += kSelThreads) c += (kb[i] == prefix && cand_ids[i] <= mid) ? 1u : 0u;
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_ntie, c);
+      __syncthreads();
+      if (s_ntie >= need) hi = mid; else lo = mid;
+    }
+    if (threadIdx.x == 0) s_id_thr = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ctl[1] = (int32_t)prefix; ctl[2] = (int32_t)need; ctl[3] = 0;
+    *reinterpret_cast<long long*>(hists) = s_id_thr;        // the histograms are consumed: their first words carry the id threshold
+  }
 }
 
 __device__ __forceinline__ uint32_t bucket_of(uint32_t flag, int log2_buckets) { return log2_buckets ? flag >> (32 - log2_buckets) : 0u; }
 
 __global__ void __launch_bounds__(256) mark_kernel(float* __restrict__ cand_keys, const int64_t* __restrict__ cand_ids, int32_t* __restrict__ ctl,
                                                    int32_t capacity, int32_t n, uint64_t seed, int32_t log2_buckets,
-                                                   uint32_t* __restrict__ bcount) {
+                                                   uint32_t* __restrict__ bcount, const uint32_t* __restrict__ hists) {
   const int m = min(ctl[0], capacity);
   if (m < n) return;
   const uint32_t T = (uint32_t)ctl[1], need_ties = (uint32_t)ctl[2];
+  const long long id_thr = *reinterpret_cast<const long long*>(hists);
   uint32_t* kb = reinterpret_cast<uint32_t*>(cand_keys);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     const uint32_t b = kb[i];
     bool sel = b < T;
-    if (b == T) sel = (uint32_t)atomicAdd(&ctl[3], 1) < need_ties;   // exact ties at the threshold: any of them (measure zero)
+    if (b == T) sel = cand_ids[i] <= id_thr && (uint32_t)atomicAdd(&ctl[3], 1) < need_ties;   // ties at the threshold: smallest ids first
     uint32_t flag = 0xFFFFFFFFu;
     if (sel) {
       flag = shuffle_hash(cand_ids[i], seed);
@@ -329,6 +377,52 @@ extern "C" int64_t angio_sample_rays_workspace_bytes(int32_t capacity, int64_t n
          align256(n * 8);
 }
 
+namespace {
+
+struct SampleWorkspace {
+  int32_t* ctl;
+  uint32_t *bcount, *bfill, *hists, *bstart, *tmp_hash;
+  float* keys;
+  int64_t *ids, *tmp_ids;
+};
+
+SampleWorkspace carve_workspace(void* workspace, int32_t capacity, int64_t n) {
+  SampleWorkspace w;
+  char* wb = reinterpret_cast<char*>(workspace);
+  const int64_t head = align256(16 + (3 * kMaxBuckets + 1 + kHistWords) * 4);
+  w.ctl = reinterpret_cast<int32_t*>(wb);
+  w.bcount = reinterpret_cast<uint32_t*>(wb + 16);
+  w.bfill = w.bcount + kMaxBuckets;
+  w.hists = w.bfill + kMaxBuckets;                                     // zeroed together with the counters
+  w.bstart = w.hists + kHistWords;
+  wb += head;
+  w.keys = reinterpret_cast<float*>(wb); wb += align256((int64_t)capacity * 4);
+  w.ids = reinterpret_cast<int64_t*>(wb); wb += align256((int64_t)capacity * 8);
+  w.tmp_hash = reinterpret_cast<uint32_t*>(wb); wb += align256(n * 4);
+  w.tmp_ids = reinterpret_cast<int64_t*>(wb);
+  return w;
+}
+
+// candidates in w.keys / w.ids, their count in w.ctl[0] -> the n smallest keys, shuffled, in ids_out
+int select_and_shuffle(const SampleWorkspace& w, int32_t capacity, int64_t n, uint64_t seed, int64_t* ids_out, int32_t* status, cudaStream_t st) {
+  int n_buckets = 1, log2b = 0;                                        // ~32 rays per shuffle bucket
+  while (n_buckets < kMaxBuckets && (int64_t)n_buckets * 32 < n) { n_buckets <<= 1; ++log2b; }
+  int sweep_blocks = angio::blocks_for(capacity, 1024);
+  if (sweep_blocks > angio::sm_count()) sweep_blocks = angio::sm_count();
+  angio::note_launch("radix_hist_kernel<0>"); radix_hist_kernel<0><<<sweep_blocks, kSelThreads, 0, st>>>(w.keys, w.ctl, capacity, (int32_t)n, w.hists);
+  angio::note_launch("radix_hist_kernel<1>"); radix_hist_kernel<1><<<sweep_blocks, kSelThreads, 0, st>>>(w.keys, w.ctl, capacity, (int32_t)n, w.hists);
+  angio::note_launch("radix_hist_kernel<2>"); radix_hist_kernel<2><<<sweep_blocks, kSelThreads, 0, st>>>(w.keys, w.ctl, capacity, (int32_t)n, w.hists);
+  angio::note_launch("select_finish_kernel"); select_finish_kernel<<<1, kSelThreads, 0, st>>>(w.ctl, capacity, (int32_t)n, w.hists, status, ids_out, w.keys, w.ids);
+  angio::note_launch("mark_kernel"); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(w.keys, w.ids, w.ctl, capacity, (int32_t)n, seed, log2b, w.bcount, w.hists);
+  angio::note_launch("scatter_kernel"); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(w.keys, w.ids, w.ctl, capacity, (int32_t)n, n_buckets, log2b, w.bcount,
+                                                                          w.bfill, w.bstart, w.tmp_hash, w.tmp_ids);
+  angio::note_launch("bucket_sort_kernel"); bucket_sort_kernel<<<angio::blocks_for(n_buckets, 8), 256, 0, st>>>(w.ctl, capacity, (int32_t)n, n_buckets, w.bstart,
+                                                                                        w.tmp_hash, w.tmp_ids, ids_out);
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n, uint64_t seed, float tau, int32_t capacity,
                                  int64_t* ids_out, int32_t* status, void* workspace, int64_t workspace_bytes, void* stream) {
   ANGIO_REQUIRE(n_pool > 0 && n > 0 && n <= n_pool && capacity >= n && tau > 0.0f && ids_out && status && workspace,
@@ -339,34 +433,29 @@ extern "C" int angio_sample_rays(const float* weights, int64_t n_pool, int64_t n
     return ANGIO_ERR_WORKSPACE;
   }
   cudaStream_t st = angio::as_stream(stream);
-  char* wb = reinterpret_cast<char*>(workspace);
-  const int64_t head = align256(16 + (3 * kMaxBuckets + 1 + kHistWords) * 4);
-  int32_t* ctl = reinterpret_cast<int32_t*>(wb);
-  uint32_t* bcount = reinterpret_cast<uint32_t*>(wb + 16);
-  uint32_t* bfill = bcount + kMaxBuckets;
-  uint32_t* hists = bfill + kMaxBuckets;                               // zeroed together with the counters
-  uint32_t* bstart = hists + kHistWords;
-  wb += head;
-  float* keys = reinterpret_cast<float*>(wb); wb += align256((int64_t)capacity * 4);
-  int64_t* ids = reinterpret_cast<int64_t*>(wb); wb += align256((int64_t)capacity * 8);
-  uint32_t* tmp_hash = reinterpret_cast<uint32_t*>(wb); wb += align256(n * 4);
-  int64_t* tmp_ids = reinterpret_cast<int64_t*>(wb);
-  ANGIO_CUDA(cudaMemsetAsync(ctl, 0, 16 + (2 * kMaxBuckets + kHistWords) * 4, st));   // counters, bucket counts / fills, radix histograms
-  if (int rc = angio_sample_candidates(weights, n_pool, seed, tau, capacity, keys, ids, ctl, stream)) return rc;
-  int n_buckets = 1, log2b = 0;                                        // ~32 rays per shuffle bucket
-  while (n_buckets < kMaxBuckets && (int64_t)n_buckets * 32 < n) { n_buckets <<= 1; ++log2b; }
-  int sweep_blocks = angio::blocks_for(capacity, 1024);
-  if (sweep_blocks > angio::sm_count()) sweep_blocks = angio::sm_count();
-  angio::note_launch("radix_hist_kernel<0>"); radix_hist_kernel<0><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch("radix_hist_kernel<1>"); radix_hist_kernel<1><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch("radix_hist_kernel<2>"); radix_hist_kernel<2><<<sweep_blocks, kSelThreads, 0, st>>>(keys, ctl, capacity, (int32_t)n, hists);
-  angio::note_launch("select_finish_kernel"); select_finish_kernel<<<1, kSelThreads, 0, st>>>(ctl, capacity, (int32_t)n, hists, status, ids_out);
-  angio::note_launch("mark_kernel"); mark_kernel<<<sweep_blocks * 4, 256, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, seed, log2b, bcount);
-  angio::note_launch("scatter_kernel"); scatter_kernel<<<sweep_blocks, kSelThreads, 0, st>>>(keys, ids, ctl, capacity, (int32_t)n, n_buckets, log2b, bcount, bfill,
-                                                                          bstart, tmp_hash, tmp_ids);
-  angio::note_launch("bucket_sort_kernel"); bucket_sort_kernel<<<angio::blocks_for(n_buckets, 8), 256, 0, st>>>(ctl, capacity, (int32_t)n, n_buckets, bstart, tmp_hash,
-                                                                                        tmp_ids, ids_out);
+  const SampleWorkspace w = carve_workspace(workspace, capacity, n);
+  ANGIO_CUDA(cudaMemsetAsync(w.ctl, 0, 16 + (2 * kMaxBuckets + kHistWords) * 4, st));   // counters, bucket counts / fills, radix histograms
+  if (int rc = angio_sample_candidates(weights, n_pool, seed, tau, capacity, w.keys, w.ids, w.ctl, stream)) return rc;
+  select_and_shuffle(w, capacity, n, seed, ids_out, status, st);
   return angio::finish_launch("angio_sample_rays");
+}
+
+extern "C" int angio_sample_select(const float* cand_keys, const int64_t* cand_ids, int32_t m, int64_t n, uint64_t seed, int64_t* ids_out,
+                                   int32_t* status, void* workspace, int64_t workspace_bytes, void* stream) {
+  ANGIO_REQUIRE(cand_keys && cand_ids && m > 0 && n > 0 && ids_out && status && workspace, "angio_sample_select: bad arguments");
+  ANGIO_REQUIRE(n <= (int64_t)1 << 24, "angio_sample_select: at most 2^24 rays per call");
+  if (workspace_bytes < angio_sample_rays_workspace_bytes(m, n)) {
+    angio::set_error("angio_sample_select: workspace too small");
+    return ANGIO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = angio::as_stream(stream);
+  const SampleWorkspace w = carve_workspace(workspace, m, n);
+  ANGIO_CUDA(cudaMemsetAsync(w.ctl, 0, 16 + (2 * kMaxBuckets + kHistWords) * 4, st));
+  ANGIO_CUDA(cudaMemcpyAsync(w.keys, cand_keys, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+  ANGIO_CUDA(cudaMemcpyAsync(w.ids, cand_ids, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+  ANGIO_CUDA(cudaMemcpyAsync(w.ctl, &m, 4, cudaMemcpyHostToDevice, st));               // pageable source: copied before the call returns
+  select_and_shuffle(w, m, n, seed, ids_out, status, st);
+  return angio::finish_launch("angio_sample_select");
 }
 
 extern "C" int angio_raygen_flat(const double* cam2world, const int64_t* ids, int64_t n, int32_t img_w, int32_t img_h, double focal,

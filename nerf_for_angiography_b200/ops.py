@@ -105,6 +105,25 @@ def sample_without_replacement(n, n_pool, weights, wsum, wsum2, seed, device, po
     return ids, status
 
 
+def sample_select(keys, cand_ids, n, seed):
+    """Check mode of the sampler: the n candidates with the smallest (positive fp32) keys, shuffled like a draw -- the selection
+    half of `sample_without_replacement` on caller-supplied race keys.  Equal keys at the threshold are taken in id order.
+    Returns (ids int64 [n], status int32 [2])."""
+    lib = _lib.load()
+    keys = _chk(keys, torch.float32, "keys", 1)
+    cand_ids = _chk(cand_ids, torch.int64, "cand_ids", 1)
+    m = keys.numel()
+    if cand_ids.numel() != m:
+        raise ValueError("keys and cand_ids must have the same length")
+    wb = int(lib.angio_sample_rays_workspace_bytes(m, int(n)))
+    ws = torch.empty((wb,), dtype=torch.uint8, device=keys.device)
+    ids = torch.empty((n,), dtype=torch.int64, device=keys.device)
+    status = torch.empty((2,), dtype=torch.int32, device=keys.device)
+    _lib.check(lib.angio_sample_select(_p(keys), _p(cand_ids), m, int(n), int(seed) & 0xFFFFFFFFFFFFFFFF, _p(ids), _p(status), _p(ws), wb,
+                                       _stream()), "angio_sample_select")
+    return ids, status
+
+
 def raygen_flat(cam2world, ids, img_w, img_h, focal, pixels=None):
     """Rays (o, d[, target pixel]) of flat ray ids (view * H * W + y * W + x): the gather that follows the sampler."""
     lib = _lib.load()

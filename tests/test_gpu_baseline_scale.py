@@ -378,6 +378,35 @@ def test_sampler_selects_exactly_the_smallest_race_keys(A):
         assert len(sure_in) >= n - 64
 
 
+def test_sampler_on_pre_drawn_keys_and_threshold_ties(A):
+    """The selection half of the sampler on PRE-DRAWN race keys (ops.sample_select): exactly numpy's n smallest keys, and when
+    several candidates share the n-th smallest key the ones with the smallest ray ids are taken -- fp32 keys tie at the threshold
+    every few hundred draws at n = 65 536, and the candidate list is in atomic-append order, so anything else would make the drawn
+    set vary from run to run."""
+    rng = np.random.default_rng(7)
+    for m, n, dup in ((5000, 1200, 0), (70_000, 65_536, 0), (5000, 1200, 7), (70_000, 65_536, 3), (3000, 100, 2500)):
+        w = (rng.random(m) ** 2 + 1e-3)
+        keys = (rng.exponential(size=m) / w).astype(np.float32)
+        ids = rng.permutation(10 * m)[:m].astype(np.int64)              # unordered, unique ray ids
+        if dup:                                                        # plant `dup` extra copies of the n-th smallest key
+            kth = np.sort(keys)[n - 1]
+            far = np.argsort(keys)[-dup:]
+            keys[far] = kth
+        got, status = A.ops.sample_select(torch.from_numpy(keys).cuda(), torch.from_numpy(ids).cuda(), n, seed=11)
+        assert status.tolist() == [m, 0]
+        got = got.cpu().numpy()
+        order = np.lexsort((ids, keys))                                 # by key, ties by ray id
+        want = ids[order[:n]]
+        assert len(np.unique(got)) == n
+        assert np.array_equal(np.sort(got), np.sort(want)), f"m={m} n={n} dup={dup}"
+        if dup:
+            kth = keys[order[n - 1]]
+            assert (keys == kth).sum() >= dup + 1 and (keys[order[n:n + 1]] == kth).all()   # the tie really straddles the threshold
+        again, _ = A.ops.sample_select(torch.from_numpy(keys).cuda(), torch.from_numpy(ids).cuda(), n, seed=11)
+        assert np.array_equal(again.cpu().numpy(), got)                 # same shuffle as well
+        assert not np.array_equal(got, np.sort(got))
+
+
 def test_sampler_inclusion_frequency_per_ray(A):
     """Per-ray inclusion frequencies of the weighted draw without replacement against numpy's sequential sampler (what pandas
     calls): 4 096 rays with weights spanning three decades, 512 per draw, 3 000 draws each side; every ray within 6 sigma."""
