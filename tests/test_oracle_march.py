@@ -172,3 +172,82 @@ def test_visibility_of_head_plus_tail_equals_full_filter():
                 keep[off[r] + j] = (T >= eps) and (a[j] >= thre)
                 T = np.float32(T * np.float32(np.float32(1.0) - a[j]))
     assert np.array_equal(keep, full)
+
+
+# ------------------------------------------------------------------------------------------------ closed form of the fp32 t-chain
+def _linear_chain(t_lo, t_hi, dt):
+    """numpy restatement of `linear_chain` (csrc/march.cu): the guard under which the marcher's t <- fl(t + dt) adds the SAME exact
+    increment at every step.  Returns the increment or None."""
+    f32 = np.float32
+    a, b = np.array([t_lo, t_hi], f32).view(np.uint32)
+    e = int(a) >> 23
+    if e != (int(b) >> 23) or e == 0 or e >= 255 or e < 24:
+        return None
+    u = np.array([(e - 23) << 23], np.uint32).view(f32)[0]           # ulp of the binade
+    s2 = f32(f32(f32(dt) / u) * f32(2.0))
+    if not s2 < f32(8388608.0):
+        return None
+    if s2 == np.floor(s2) and np.fmod(s2, f32(2.0)) == 1.0:          # dt / ulp ends in .5: round-to-even would depend on t
+        return None
+    delta = f32(f32(f32(t_lo) + f32(dt)) - f32(t_lo))
+    return delta if delta > 0 else None
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(24, 200), st.floats(0.0, 1.0), st.floats(1e-4, 0.2), st.integers(1, 4000))
+def test_closed_form_t_chain_matches_serial_fp32(expo, frac, rel_dt, k):
+    """The warp-per-ray march passes compute sample k of a run as (t1 + (k-1) D, t1 + k D) instead of replaying
+    t0 <- t1, t1 <- fl(t0 + dt) k times.  Inside one fp32 binade and under the guard this is the same bit pattern: every value is
+    a multiple of the binade's ulp, D = fl(t + dt) - t does not depend on t, and the products / sums are exact."""
+    f32 = np.float32
+    lo = f32(2.0) ** f32(expo - 127)
+    t0 = f32(lo * f32(1.0 + 0.5 * frac))                              # somewhere in the lower half of the binade
+    dt = f32(lo * f32(rel_dt) / f32(16.0))
+    t_end = f32(t0 + f32(k + 2) * dt)
+    D = _linear_chain(t0, t_end, dt)
+    if D is None:
+        return                                                         # outside the guard the kernels walk serially
+    a, b = t0, f32(t0 + dt)                                            # serial walk
+    for _ in range(k):
+        a, b = b, f32(b + dt)
+    t1 = f32(t0 + dt)
+    ca = f32(t1 + f32(f32(k - 1) * D))
+    cb = f32(t1 + f32(f32(k) * D))
+    assert a.view(np.uint32) == ca.view(np.uint32) and b.view(np.uint32) == cb.view(np.uint32)
+
+
+def test_closed_form_guard_rejects_round_to_even_ties_and_binade_crossings():
+    f32 = np.float32
+    u = f32(2.0) ** f32(10 - 23)                                       # ulp of [1024, 2048)
+    assert _linear_chain(f32(1400.0), f32(1600.0), f32(2.0 / 3.0)) is not None      # the benchmark geometry
+    assert _linear_chain(f32(1400.0), f32(1600.0), f32(100.5) * u) is None          # dt / ulp = 100.5: a tie at every step
+    assert _linear_chain(f32(900.0), f32(1100.0), f32(2.0 / 3.0)) is None           # crosses 1024
+    assert _linear_chain(f32(1400.0), f32(1600.0), f32(0.0)) is None                # no progress
+    # the tie case really is t-dependent (that is why it is excluded): fl(t + 100.5 u) - t differs between even and odd t / u
+    t_even, t_odd = f32(1400.0), f32(1400.0) + u
+    d = f32(100.5) * u
+    assert f32(f32(t_even + d) - t_even) != f32(f32(t_odd + d) - t_odd)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.floats(0.0, 1.0), st.floats(0.0, 40.0), st.sampled_from([2.0 / 3.0, 0.4, 0.2, 1.25]))
+def test_closed_form_empty_space_skip_matches_serial_fp32(frac, gap, dt):
+    """Empty-space skipping (`march_count_warp_kernel`): the serial marcher adds dt to the midpoint until it reaches the next voxel
+    boundary; in one binade that is j = max(1, ceil((target - t) / D)) steps, computed exactly on multiples of the ulp."""
+    f32 = np.float32
+    dt = f32(dt)
+    D = _linear_chain(f32(1400.0), f32(1600.0), dt)
+    assert D is not None
+    u = f32(2.0) ** f32(10 - 23)
+    tm = f32(f32(1400.0) + f32(150.0 * frac))
+    target = f32(tm + f32(gap))
+    t = tm                                                             # serial: do { t += dt } while (t < target)
+    while True:
+        t = f32(t + dt)
+        if not t < target:
+            break
+    diff = int(np.rint(f32(f32(target - tm) / u)))
+    Di = int(np.rint(f32(D / u)))
+    j = max(1, (diff + Di - 1) // Di)
+    closed = f32(tm + f32(f32(j) * D))
+    assert t.view(np.uint32) == closed.view(np.uint32)
