@@ -206,8 +206,9 @@ def build_rooflines(timeline, cnt, w, peaks, world):
         "mlp_wgrad_tc_kernel": ("tensor", flop * kept, f"weight gradients, 2*MAC per kept sample; streams {img_bytes + delta_bytes} B/sample (HBM-bound by design)"),
         "mlp_fwd_tc_kernel<SIGMA>": ("tensor", flop * cnt["grid_cells"], "occupancy-grid refresh (amortised over 16 steps)"),
         "march_head_kernel": ("hbm", 24 * R + 12 * head, "24 B/ray in, 12 B/head sample out"),
-        "march_count_kernel": ("hbm", 28 * R, "serial per-ray walk (latency-bound): 24 B/ray in, 4 B/ray out"),
-        "march_write_kernel": ("hbm", 12 * tail + 4 * R, "12 B/tail sample out"),
+        "march_count_warp_kernel": ("hbm", 28 * R + 72 * R, "warp per ray, 32 candidate samples per grid look-up round (latency-bound): 24 B/ray in, 4 B/ray + run table out"),
+        "march_write_runs_kernel": ("hbm", 12 * tail + 4 * R, "warp per ray from the run table: 12 B/tail sample out"),
+        "march_count_kernel": ("hbm", 8 * R, "stores t_min / t_max; serial walk only for rays whose t-chain crosses an fp32 binade (none here)"),
         "visibility_head_mask_kernel": ("hbm", 5 * head + 12 * R, "4 B/sample in, 1 B/sample out"),
         "visibility_mask_kernel": ("hbm", 5 * tail + 8 * R, "4 B/sample in, 1 B/sample out"),
         "compact_head_tail_kernel": ("hbm", 1 * marched + 20 * kept + 8 * R, "1 B/marched sample + 8 B/kept in, 12 B/kept out"),
@@ -223,7 +224,7 @@ def build_rooflines(timeline, cnt, w, peaks, world):
         for k in [k for k in spec if k.startswith(a)]:
             spec[k.replace(a, b)] = spec[k]
     if tail == 0.0:       # one-sync path: full march (count + write) and a two-phase visibility pass over it
-        spec["march_write_kernel"] = ("hbm", 12 * marched + 4 * R, "12 B/sample out")
+        spec["march_write_runs_kernel"] = ("hbm", 12 * marched + 4 * R, "warp per ray from the run table: 12 B/sample out")
         spec["visibility_mask_kernel"] = ("hbm", 5 * marched + 8 * R, "4 B/sample in, 1 B/sample out")
         spec["compact_kernel"] = ("hbm", 1 * marched + 20 * kept + 8 * R, "1 B/marched sample + 8 B/kept in, 12 B/kept out")
     out = []
