@@ -156,6 +156,46 @@ def _is_fused_model(m):
     return isinstance(m, CPPN)
 
 
+class PackedRayIndices(torch.Tensor):
+    """nerfacc's `ray_indices` (int64 ray id per sample, sorted by ray) that also carries the packed layout it came from: the
+    segment offsets [n_rays + 1] int32 and the int32 index vector the kernels read.  `acc_render_volume_density` and the fused
+    model queries take them from here instead of rebuilding the offsets with a search (and a synchronising sortedness check).
+
+    Copies that keep every sample in place (`clone`, `detach`, `contiguous`, `long`, same-dtype / same-device `to`) keep the layout;
+    anything else -- slicing, masking, arithmetic, using it as an index -- returns a plain tensor."""
+
+    _KEEP = ("clone", "detach", "contiguous", "long", "to", "cuda")
+
+    @staticmethod
+    def wrap(ray_indices, offsets, idx32):
+        t = ray_indices.as_subclass(PackedRayIndices)
+        t._angio_offsets = offsets
+        t._angio_idx32 = idx32
+        return t
+
+    def __deepcopy__(self, memo):
+        off, i32 = getattr(self, "_angio_offsets", None), getattr(self, "_angio_idx32", None)
+        plain = self.as_subclass(torch.Tensor).clone()
+        return plain if off is None else PackedRayIndices.wrap(plain, off.clone(), i32.clone())
+
+    def __reduce_ex__(self, proto):                    # pickles / torch.save as the plain index tensor
+        return self.as_subclass(torch.Tensor).__reduce_ex__(proto)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        with torch._C.DisableTorchFunctionSubclass():
+            out = func(*args, **kwargs)
+        src = args[0] if args and isinstance(args[0], cls) else None
+        if (src is not None and isinstance(out, torch.Tensor) and getattr(func, "__name__", "") in cls._KEEP
+                and out.shape == src.shape and out.dtype == src.dtype and out.device == src.device
+                and getattr(src, "_angio_offsets", None) is not None):
+            return cls.wrap(out.as_subclass(torch.Tensor), src._angio_offsets, src._angio_idx32)
+        if isinstance(out, cls):                       # never leak the subclass (and stale offsets) into derived tensors
+            out = out.as_subclass(torch.Tensor)
+        return out
+
+
 @torch.no_grad()
 def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=None, sigma_fn=None, alpha_fn=None,
                  early_stop_eps=1e-4, alpha_thre=0.0, near_plane=None, far_plane=None, render_step_size=1e-3,
@@ -196,8 +236,6 @@ def ray_marching(rays_o, rays_d, t_min=None, t_max=None, scene_aabb=None, grid=N
             alphas = fn(t0[:, None], t1[:, None], ray_idx.long()).reshape(-1).contiguous().float()
         thre = min(float(alpha_thre), float(grid.occs_mean_host))
         ray_idx, t0, t1, offsets, _ = ops.visibility_compact(alphas, offsets, t0, t1, early_stop_eps, thre)
-    ray_indices = ray_idx.long()
-    ray_indices._angio_offsets = offsets      # packed segment offsets ride along for the compositor
-    ray_indices._angio_idx32 = ray_idx
+    ray_indices = PackedRayIndices.wrap(ray_idx.long(), offsets, ray_idx)   # the packed layout rides along for the compositor
     out = (ray_indices, t0[:, None], t1[:, None])
     return out + (offsets,) if return_offsets else out
